@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Benchmark of the CenterNet heatmap hot path (render + loss + decode) — BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+One "step" = one pass of the hot path over one batch of synthetic input of BASELINE.json configs[1]
+("CenterNet 2D-OD full heatmap path (render+loss+decode) batch 256 on 1xB200": 10 classes, 128x384 heatmaps, 32 objects per
+image, top-K = 100).  Under torchrun (N > 1) every rank owns its own 256 images (weak scaling; N = 8 is configs[2]'s
+2048-image batch), the only collective is the all-reduce of the 16 loss partials, timing is barrier + device events,
+max over ranks.  Rank 0 prints ONE JSON line.
+
+`--impl reference` times the reference's CPU implementation of the same path on the host cores: /root/reference (pure
+Python/numba/TF) cannot travel to the GPU box and TF is not installed, so this is the oracle port (oracle/: NumPy
+restatement; C + OpenMP restatement when built), on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "computer-vision-models_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+H, W, NB_CLASSES, N_OBJ, TOPK = 128, 384, 10, 32, 100
+CONFIG_ID = 2
+
+
+def gen_objects(first_image, B):
+    """per-image rng = default_rng(1234 + 1000*config + image_index); boxes in input px, inside the image."""
+    R = 2
+    in_w, in_h = W * R, H * R
+    boxes = np.zeros((B, N_OBJ, 4), np.float64)
+    cls = np.zeros((B, N_OBJ), np.int32)
+    ign = np.zeros((B, 2, 4), np.float64)
+    for i in range(B):
+        rng = np.random.default_rng(1234 + 1000 * CONFIG_ID + first_image + i)
+        w = np.exp(rng.uniform(np.log(4), np.log(160), N_OBJ))
+        h = np.exp(rng.uniform(np.log(4), np.log(96), N_OBJ))
+        cx, cy = rng.uniform(0, in_w, N_OBJ), rng.uniform(0, in_h, N_OBJ)
+        x0, y0 = np.maximum(0, cx - w / 2), np.maximum(0, cy - h / 2)
+        x1, y1 = np.minimum(in_w, cx + w / 2), np.minimum(in_h, cy + h / 2)
+        boxes[i] = np.stack([x0, y0, x1 - x0, y1 - y0], axis=1)
+        cls[i] = rng.integers(0, NB_CLASSES, N_OBJ)
+        ign[i] = np.stack([rng.uniform(0, W - 4, 2), rng.uniform(0, H - 4, 2), rng.uniform(1, 12, 2), rng.uniform(1, 8, 2)], axis=1)
+    return boxes, cls, ign
+
+
+def centres(boxes):
+    cx = np.clip(((boxes[..., 0] + boxes[..., 2] / 2) / 2).astype(np.int64), 0, W - 1)
+    cy = np.clip(((boxes[..., 1] + boxes[..., 3] / 2) / 2).astype(np.int64), 0, H - 1)
+    return cx, cy
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_port_step(n_images, first_image=0):
+    """The oracle port of the path on `n_images` images of the same workload; returns seconds (render, loss, decode)."""
+    from oracle import decode_np, loss_np, render_np
+    from oracle.layout import make_layout
+    Lo = make_layout(H, W, NB_CLASSES, "N")
+    boxes, cls, ign = gen_objects(first_image, n_images)
+    rng = np.random.default_rng(99)
+    yp = np.zeros((n_images, H, W, Lo.Cp), np.float32)
+    yp[..., :NB_CLASSES] = 1.0 / (1.0 + np.exp(-rng.normal(-4.0, 1.5, (n_images, H, W, NB_CLASSES))))
+    yp[..., NB_CLASSES:] = rng.uniform(0, 60, (n_images, H, W, Lo.Cp - NB_CLASSES))
+    t0 = time.perf_counter()
+    yt = np.stack([render_np.render_image(Lo, boxes[i], cls[i], ign[i]) for i in range(n_images)])
+    t1 = time.perf_counter()
+    loss_np.total_loss(Lo, yt, yp)
+    t2 = time.perf_counter()
+    decode_np.decode_topk(Lo, yp, TOPK)
+    t3 = time.perf_counter()
+    return t1 - t0, t2 - t1, t3 - t2
+
+
+def run_reference(args):
+    """Reference arm: the CPU port on the host cores.  Under torchrun only rank 0 works."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    n = 8  # bounded sample per step: BASELINE configs[0]'s batch
+    for _ in range(args.warmup):
+        cpu_port_step(n)
+    ts = [cpu_port_step(n) for _ in range(args.steps)]
+    tot = float(np.sum(ts))
+    value = n * args.steps / tot
+    line = {
+        "impl": "reference", "metric": "images/sec (heatmap render+loss+decode)", "value": value, "unit": "images/sec",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "CenterNet 2D-OD full heatmap path (render+loss+decode), 10-class 128x384, 32 obj/img, top-K=100",
+                   "batch_per_step": n, "note": "bounded sample of configs[1] (same per-image work)"},
+        "cpu_baseline": {"value": value, "unit": "images/sec", "cores": 1, "kind": "port",
+                         "sample": f"{n} images/step x {args.steps} steps, NumPy oracle port (TF/numba reference cannot run on the box)"},
+        "e2e": {"value": value, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "stages_s_per_image": {k: float(np.sum([t[i] for t in ts]) / (n * args.steps)) for i, k in enumerate(("render", "loss", "decode"))},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cvmhot import dist as cdist
+    from cvmhot import ops
+    from cvmhot.layout import layout_from_params
+    from cvmhot.models.centernet import CenternetParams
+    from cvmhot.models.centernet.processor import pack_boxes, pack_objects
+
+    rank, world, local = cdist.init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = args.batch
+
+    p = CenternetParams(NB_CLASSES, per_class_heatmap=True)
+    p.INPUT_HEIGHT, p.INPUT_WIDTH = H * 2, W * 2
+    L = layout_from_params(p)
+    assert (L.Cp, L.Ct) == (14, 15)
+
+    # ---- synthetic inputs, resident in HBM before the timed region ----
+    boxes, cls, ign = gen_objects(rank * B, B)
+    rec, offs = pack_objects(list(boxes), list(cls))
+    ign_rec, ign_offs = pack_boxes(list(ign))
+    objs_d = ops.to_device_records(rec, ops.OBJ_DTYPE, dev)
+    offs_d = torch.from_numpy(offs).to(dev)
+    ign_d = ops.to_device_records(ign_rec, ops.BOX_DTYPE, dev)
+    ioffs_d = torch.from_numpy(ign_offs).to(dev)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    y_pred = torch.empty((B, H, W, L.Cp), dtype=torch.float32, device=dev)
+    y_pred[..., :L.hm] = torch.sigmoid(torch.randn((B, H, W, L.hm), device=dev, generator=g) * 1.5 - 4.0)
+    y_pred[..., L.off_roff:L.off_roff + 2] = torch.rand((B, H, W, 2), device=dev, generator=g)
+    y_pred[..., L.off_box:L.off_box + 2] = torch.rand((B, H, W, 2), device=dev, generator=g) * 120 + 4
+    cx, cy = centres(boxes)
+    bi = np.repeat(np.arange(B), N_OBJ)
+    peak = torch.rand(B * N_OBJ, device=dev, generator=g) * 0.69 + 0.3
+    y_pred[torch.from_numpy(bi).to(dev), torch.from_numpy(cy.reshape(-1)).to(dev), torch.from_numpy(cx.reshape(-1)).to(dev),
+           torch.from_numpy(cls.reshape(-1).astype(np.int64)).to(dev)] = peak
+    y_true = torch.empty((B, H, W, L.Ct), dtype=torch.float32, device=dev)
+    partials = torch.empty(16, dtype=torch.float64, device=dev)
+    loss_out = torch.zeros(10, dtype=torch.float32, device=dev)
+
+    bytes_render = 4 * H * W * L.Ct * B
+    bytes_loss = 4 * H * W * (L.Ct + L.Cp) * B
+    bytes_decode = 4 * H * W * L.Cp * B
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(events=None):
+        if events is not None:
+            events[0].record()
+        ops.render_gt(L, objs_d, offs_d, B, ign_d, ioffs_d, out=y_true)
+        if events is not None:
+            events[1].record()
+        ops.loss_partials(L, y_true, y_pred, True, out=partials)
+        if world > 1:
+            dist.all_reduce(partials)
+        ops.loss_finalize(L, partials, out=loss_out)
+        if events is not None:
+            events[2].record()
+        out = ops.decode_topk(L, y_pred, K=TOPK)
+        if events is not None:
+            events[3].record()
+        return out
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: device-resident inputs (`value`) ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    stage_events = [[ev() for _ in range(4)] for _ in range(args.steps)]
+    barrier()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for k in range(args.steps):
+        out = step(stage_events[k])
+    e1.record()
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    stage_ms = np.array([[s[i].elapsed_time(s[i + 1]) for i in range(3)] for s in stage_events]).mean(axis=0)
+
+    # ---- e2e: the same step through the public API with HOST buffers (pinned), copies inside the timed region ----
+    rec_h = torch.from_numpy(rec.view(np.uint8).reshape(-1)).pin_memory()
+    ign_h = torch.from_numpy(ign_rec.view(np.uint8).reshape(-1)).pin_memory()
+    offs_h, ioffs_h = torch.from_numpy(offs).pin_memory(), torch.from_numpy(ign_offs).pin_memory()
+    y_pred_h = torch.empty(y_pred.shape, dtype=torch.float32).pin_memory()
+    y_pred_h.copy_(y_pred)
+    res_h = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items() if v is not None}
+    loss_h = torch.empty(10, dtype=torch.float32).pin_memory()
+    h2d = rec_h.numel() + ign_h.numel() + offs_h.numel() * 4 + ioffs_h.numel() * 4 + y_pred_h.numel() * 4
+    d2h = loss_h.numel() * 4 + sum(v.numel() * v.element_size() for v in res_h.values())
+    y_pred_in = torch.empty_like(y_pred)
+
+    def e2e_step():
+        o_d = rec_h.to(dev, non_blocking=True)
+        of_d = offs_h.to(dev, non_blocking=True)
+        i_d = ign_h.to(dev, non_blocking=True)
+        if_d = ioffs_h.to(dev, non_blocking=True)
+        ops.render_gt(L, o_d, of_d, B, i_d, if_d, out=y_true)
+        y_pred_in.copy_(y_pred_h, non_blocking=True)
+        ops.loss_partials(L, y_true, y_pred_in, True, out=partials)
+        if world > 1:
+            dist.all_reduce(partials)
+        ops.loss_finalize(L, partials, out=loss_out)
+        o = ops.decode_topk(L, y_pred_in, K=TOPK)
+        loss_h.copy_(loss_out, non_blocking=True)
+        for k_, v in res_h.items():
+            v.copy_(o[k_], non_blocking=True)
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    f0, f1 = ev(), ev()
+    f0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    e2e_ms = f0.elapsed_time(f1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * B * args.steps / (elapsed_ms * 1e-3)
+    e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
+    peak_gbs, peak_src = load_peaks()
+    names = ["render_kernel", "loss_fwd_kernel", "decode_stream_kernel"]
+    sbytes = [bytes_render, bytes_loss, bytes_decode]
+    dom = int(np.argmax(stage_ms))
+    achieved = sbytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
+    whole = sum(sbytes) / (elapsed_ms / args.steps * 1e-3) / 1e9
+
+    # CPU baseline (reported only): oracle port on a bounded sample, rank 0, N = 1 only
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        n_cpu = 8
+        cpu_port_step(1)
+        ts = cpu_port_step(n_cpu)
+        cpu = {"value": n_cpu / sum(ts), "unit": "images/sec", "cores": 1, "kind": "port",
+               "sample": f"{n_cpu} images of the same workload (configs[0] batch), NumPy oracle port; "
+                         f"render {ts[0]:.2f}s loss {ts[1]:.2f}s decode {ts[2]:.2f}s"}
+
+    line = {
+        "metric": "images/sec (heatmap render+loss+decode)", "value": value, "unit": "images/sec", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "CenterNet 2D-OD full heatmap path (render+loss+decode), 10-class 128x384, 32 obj/img, top-K=100 (BASELINE configs[1])",
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world} (batch shards, one 128-byte all-reduce)",
+                   "l2": "inputs larger than L2 (y_pred 705 MB + y_true 755 MB per GPU per step)"},
+        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                     "whole_step_gbs": whole, "whole_step_frac": whole / peak_gbs,
+                     "stages": {n: {"ms": float(m), "gbs": b / (m * 1e-3) / 1e9, "frac": b / (m * 1e-3) / 1e9 / peak_gbs}
+                                for n, m, b in zip(names, stage_ms, sbytes)}},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps, "note": "host pinned buffers -> public API -> host results, copies inside the timed region"},
+        "gpu_launches": 6 * args.steps,
+        "clocks": clocks,
+        "loss": float(loss_out[0]),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,597 @@
+// Fused CenterNet / CenterTracker loss forward: ONE streaming pass over y_true and y_pred.
+//
+// Replaces the ~60 eager TF ops of CenternetLoss.call (reference models/centernet/loss.py:31-60,107-155) and
+// CentertrackerLoss.track_offset_loss (models/centertracker/loss.py:16-28).  Bound: HBM.  Algorithmic bytes per pixel:
+// 4*(y_true_stride + y_pred_stride).
+//
+// Structure (Blackwell): persistent CTAs; thread 0 streams spans of TP pixels of both tensors into a 3-stage shared
+// memory ring with 1-D bulk async copies (cp.async.bulk -> UBLKCP, completion on an mbarrier), so no registers are
+// tied up by loads in flight; all 256 threads consume a stage with a heatmap-element-flat mapping (bank conflicts
+// <= 2-way for any channel stride).  Per-thread fp32 sums live for one span only and are folded into fp64 per-thread
+// accumulators; warp shuffle -> per-block partials -> a fixed-order second kernel.  No float atomics: results are
+// bit-reproducible run to run.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kStages = 3;
+
+struct LossParams {
+    const float* yt;
+    const float* yp;
+    long long n_pixels;
+    long long n_spans;
+    int TP;            // pixels per span (multiple of 4)
+    int st_t, st_p;    // per-pixel strides in floats
+    int hm;
+    int wch;           // weights channel inside a y_true pixel, -1 = unweighted (metric mode, loss.py:55-57)
+    float inv_hm;
+    float fa, fb;
+    int a_is2, b_is4;
+    int n_fields;
+    int f_off[CVM_MAX_FIELDS], f_size[CVM_MAX_FIELDS], f_kind[CVM_MAX_FIELDS];
+    int use_bulk;
+    double* block_partials;   // [gridDim.x][CVM_NPART]
+};
+
+__device__ __forceinline__ float pow_a(float x, const LossParams& p) { return p.a_is2 ? x * x : powf(x, p.fa); }
+__device__ __forceinline__ float pow_b(float x, const LossParams& p) {
+    if (p.b_is4) {
+        float x2 = x * x;
+        return x2 * x2;
+    }
+    return powf(x, p.fb);
+}
+
+// one regression field at a peak pixel: sum_k |term| (loss.py:115-128), fp64 from fp32 inputs
+__device__ double field_term(int kind, const float* t, const float* q, int size) {
+    double s = 0.0;
+    if (kind == CVM_KIND_CE) {
+        // -sum_c t_c * log_softmax(q)_c, labels not renormalised (categorical_crossentropy from_logits, loss.py:122)
+        double mx = -1e300;
+        for (int k = 0; k < size; ++k) mx = fmax(mx, (double)q[k]);
+        double se = 0.0;
+        for (int k = 0; k < size; ++k) se += exp((double)q[k] - mx);
+        const double lse = mx + log(se);
+        for (int k = 0; k < size; ++k) s += (double)t[k] * (lse - (double)q[k]);
+        return fabs(s);
+    }
+    for (int k = 0; k < size; ++k) {
+        const double d = (double)t[k] - (double)q[k];
+        if (kind == CVM_KIND_MSE)
+            s += d * d;
+        else if (kind == CVM_KIND_MAE)
+            s += fabs(d);
+        else
+            s += fabs(d / fmax(fabs((double)t[k]), 1.0));
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(kThreads) loss_fwd_kernel(const LossParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full_bar[kStages];
+    __shared__ double red[kThreads / 32][CVM_NPART];
+
+    float* const ring = reinterpret_cast<float*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int TP = p.TP;
+    const size_t t_floats = (size_t)TP * p.st_t;
+    const size_t stage_floats = (size_t)TP * (p.st_t + p.st_p);
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // a span can use the bulk-copy engine when it is full (TP % 4 == 0 keeps 16-byte granularity) and pointers are aligned
+    auto span_pixels = [&](long long span) -> int {
+        const long long left = p.n_pixels - span * TP;
+        return left < TP ? (int)left : TP;
+    };
+    auto span_is_bulk = [&](long long span) -> bool { return p.use_bulk && span_pixels(span) == TP; };
+    auto load_span = [&](long long span, int s) {
+        float* dst_t = ring + (size_t)s * stage_floats;
+        float* dst_p = dst_t + t_floats;
+        const float* src_t = p.yt + span * (long long)TP * p.st_t;
+        const float* src_p = p.yp + span * (long long)TP * p.st_p;
+        if (span_is_bulk(span)) {
+            if (tid == 0) {
+                const uint32_t bt = (uint32_t)(t_floats * 4), bp = (uint32_t)((size_t)TP * p.st_p * 4);
+                mbar_arrive_expect_tx(&full_bar[s], bt + bp);
+                bulk_g2s(dst_t, src_t, bt, &full_bar[s]);
+                bulk_g2s(dst_p, src_p, bp, &full_bar[s]);
+            }
+        } else {  // ragged tail / unaligned tensors: cooperative copy, published by the __syncthreads in wait_span
+            const int np = span_pixels(span);
+            for (int i = tid; i < np * p.st_t; i += kThreads) dst_t[i] = src_t[i];
+            for (int i = tid; i < np * p.st_p; i += kThreads) dst_p[i] = src_p[i];
+        }
+    };
+
+    const long long gstride = gridDim.x;
+    for (int s = 0; s < kStages; ++s) {
+        const long long span = blockIdx.x + (long long)s * gstride;
+        if (span < p.n_spans) load_span(span, s);
+    }
+
+    double accP = 0.0, accN = 0.0, accF[CVM_MAX_FIELDS];
+#pragma unroll
+    for (int f = 0; f < CVM_MAX_FIELDS; ++f) accF[f] = 0.0;
+    unsigned int n_pos = 0, n_obj = 0;
+    uint32_t phase_bits = 0;
+
+    const int hm = p.hm, st_t = p.st_t, st_p = p.st_p, wch = p.wch;
+
+    for (int it = 0;; ++it) {
+        const long long span = blockIdx.x + (long long)it * gstride;
+        if (span >= p.n_spans) break;
+        const int s = it % kStages;
+        if (span_is_bulk(span)) {
+            mbar_wait(&full_bar[s], (phase_bits >> s) & 1u);
+            phase_bits ^= (1u << s);
+        } else {
+            __syncthreads();
+        }
+        const float* __restrict__ T = ring + (size_t)s * stage_floats;
+        const float* __restrict__ Q = T + t_floats;
+        const int ne = span_pixels(span) * hm;
+
+        float sP = 0.f, sN = 0.f;
+#pragma unroll 4
+        for (int j = tid; j < ne; j += kThreads) {
+            int px, c;
+            if (hm == 1) {
+                px = j;
+                c = 0;
+            } else {
+                px = __float2int_rz(((float)j + 0.5f) * p.inv_hm);
+                c = j - px * hm;
+            }
+            const float y = T[px * st_t + c];
+            const float q = Q[px * st_p + c];
+            const float w = wch >= 0 ? T[px * st_t + wch] : 1.0f;
+            if (y < 1.0f) {  // neg_mask (loss.py:36,43-48)
+                const float l = logf(fminf(fmaxf(1.0f - q, 0.01f), 0.99f));
+                sN += (-(pow_b(1.0f - y, p) * pow_a(q, p)) * l) * w;
+            } else if (y == 1.0f) {  // pos_mask (loss.py:35,38-42)
+                const float l = logf(fminf(fmaxf(q, 0.01f), 0.99f));
+                sP += (-pow_a(1.0f - q, p) * l) * w;
+                ++n_pos;
+                // the lowest heatmap channel holding a 1.0 owns the pixel's regression terms (pos_mask reduce_max, loss.py:110-113)
+                bool owner = true;
+                for (int c2 = 0; c2 < c; ++c2) owner = owner && !(T[px * st_t + c2] == 1.0f);
+                if (owner) {
+                    ++n_obj;
+#pragma unroll
+                    for (int f = 0; f < CVM_MAX_FIELDS; ++f)
+                        if (f < p.n_fields)
+                            accF[f] += field_term(p.f_kind[f], T + px * st_t + p.f_off[f], Q + px * st_p + p.f_off[f],
+                                                  p.f_size[f]);
+                }
+            }
+        }
+        accP += (double)sP;
+        accN += (double)sN;
+
+        __syncthreads();  // everyone is done with stage s
+        const long long next = span + (long long)kStages * gstride;
+        if (next < p.n_spans) load_span(next, s);
+    }
+
+    // block reduction: warp shuffles in fp64, then a fixed-order sum over the 8 warps
+    double v[CVM_NPART];
+    v[0] = accP;
+    v[1] = accN;
+    v[2] = (double)n_pos;
+    v[3] = (double)n_obj;
+#pragma unroll
+    for (int f = 0; f < CVM_MAX_FIELDS; ++f) v[4 + f] = accF[f];
+#pragma unroll
+    for (int k = 4 + CVM_MAX_FIELDS; k < CVM_NPART; ++k) v[k] = 0.0;
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int k = 0; k < CVM_NPART; ++k) {
+        const double r = warp_sum(v[k]);
+        if (lane == 0) red[warp][k] = r;
+    }
+    __syncthreads();
+    if (tid < CVM_NPART) {
+        double r = 0.0;
+        for (int wi = 0; wi < kThreads / 32; ++wi) r += red[wi][tid];
+        p.block_partials[(size_t)blockIdx.x * CVM_NPART + tid] = r;
+    }
+}
+
+// fixed-order reduction of the per-block partials -> partials[CVM_NPART]
+__global__ void __launch_bounds__(256) loss_reduce_kernel(const double* __restrict__ block_partials, int n_blocks,
+                                                          double* __restrict__ partials) {
+    __shared__ double sh[16][CVM_NPART];
+    const int k = threadIdx.x % CVM_NPART, g = threadIdx.x / CVM_NPART;  // 16 groups
+    double r = 0.0;
+    for (int b = g; b < n_blocks; b += 16) r += block_partials[(size_t)b * CVM_NPART + k];
+    sh[g][k] = r;
+    __syncthreads();
+    if (threadIdx.x < CVM_NPART) {
+        double t = 0.0;
+        for (int gi = 0; gi < 16; ++gi) t += sh[gi][threadIdx.x];
+        partials[threadIdx.x] = t;
+    }
+}
+
+struct FinalizeParams {
+    int n_fields;
+    int f_post[CVM_MAX_FIELDS];
+    float f_weight[CVM_MAX_FIELDS];
+};
+
+// loss.py:59 (tf.cond n>0), :130, :98 (orientation), :140-153 (weighting)
+__global__ void loss_finalize_kernel(const double* __restrict__ part, float* __restrict__ out, const FinalizeParams fp) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double P = part[0], N = part[1], n = part[2], nobj = part[3];
+    const double focal = n > 0.0 ? (P + N) / n : N;
+    double total = focal;
+    out[1] = (float)focal;
+    for (int f = 0; f < fp.n_fields; ++f) {
+        double v = nobj > 0.0 ? part[4 + f] / nobj : part[4 + f];
+        if (fp.f_post[f] == CVM_POST_ORIENT) v = sqrt(1.0 - 0.99 * cos(2.0 * v)) + fabs(v * v * 0.05) - 0.0999;
+        out[2 + f] = (float)v;
+        total += v * (double)fp.f_weight[f];
+    }
+    out[0] = (float)total;
+}
+
+int pick_span_pixels(int st_t, int st_p, size_t* smem_bytes) {
+    // keep the 3-stage ring around <= 96 KB so two CTAs fit per SM
+    int TP = 256;
+    while (TP > 16 && (size_t)kStages * TP * (st_t + st_p) * 4 > 96 * 1024) TP >>= 1;
+    *smem_bytes = (size_t)kStages * TP * (st_t + st_p) * 4;
+    return TP;
+}
+
+int loss_grid(long long n_spans, size_t smem_bytes) {
+    int per_sm = (int)((220 * 1024) / (smem_bytes + 2048));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    long long g = (long long)cvm_num_sms() * per_sm;
+    if (g > n_spans) g = n_spans;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+int check_layout_for_loss(const cvm_layout* L, int st_t, int st_p) {
+    CVM_CHECK_ARG(L != nullptr, "layout is NULL");
+    CVM_CHECK_ARG(L->hm >= 1 && L->hm <= 64, "hm=%d out of range [1,64]", L->hm);
+    CVM_CHECK_ARG(L->Cp >= L->hm && L->Ct == L->Cp + 1, "need Cp >= hm and Ct == Cp+1 (Cp=%d Ct=%d hm=%d)", L->Cp, L->Ct, L->hm);
+    CVM_CHECK_ARG(st_t >= L->Ct && st_p >= L->Cp, "strides (%d,%d) smaller than channel counts (%d,%d)", st_t, st_p, L->Ct, L->Cp);
+    CVM_CHECK_ARG(st_t <= 256 && st_p <= 256, "pixel strides above 256 floats are not supported");
+    CVM_CHECK_ARG(L->n_fields >= 0 && L->n_fields <= CVM_MAX_FIELDS, "n_fields=%d", L->n_fields);
+    for (int f = 0; f < L->n_fields; ++f) {
+        CVM_CHECK_ARG(L->field_off[f] >= L->hm && L->field_off[f] + L->field_size[f] <= L->Cp && L->field_size[f] >= 1,
+                      "field %d [%d,%d) outside [hm,Cp)", f, L->field_off[f], L->field_off[f] + L->field_size[f]);
+        CVM_CHECK_ARG(L->field_kind[f] >= 0 && L->field_kind[f] <= 3, "field %d: unknown kind %d", f, L->field_kind[f]);
+    }
+    return CVM_OK;
+}
+
+}  // namespace
+
+extern "C" size_t cvm_loss_workspace_bytes(const cvm_layout* L, long long n_pixels) {
+    (void)L;
+    (void)n_pixels;
+    // per-block partials for the largest grid we ever launch (4 CTAs/SM)
+    return (size_t)cvm_num_sms() * 4 * CVM_NPART * sizeof(double);
+}
+
+extern "C" int cvm_loss_fwd(const cvm_layout* L, const float* y_true, int y_true_stride, const float* y_pred,
+                            int y_pred_stride, long long n_pixels, int use_weights, double* partials, void* ws,
+                            size_t ws_bytes, void* stream) {
+    int rc = check_layout_for_loss(L, y_true_stride, y_pred_stride);
+    if (rc != CVM_OK) return rc;
+    CVM_CHECK_ARG(y_true && y_pred && partials && ws, "NULL pointer argument");
+    CVM_CHECK_ARG(n_pixels >= 0, "n_pixels < 0");
+    if (ws_bytes < cvm_loss_workspace_bytes(L, n_pixels)) {
+        cvm_set_error("workspace too small: %zu < %zu", ws_bytes, cvm_loss_workspace_bytes(L, n_pixels));
+        return CVM_ERR_WS;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+    LossParams p;
+    memset(&p, 0, sizeof(p));
+    size_t smem = 0;
+    p.TP = pick_span_pixels(y_true_stride, y_pred_stride, &smem);
+    p.yt = y_true;
+    p.yp = y_pred;
+    p.n_pixels = n_pixels;
+    p.n_spans = (n_pixels + p.TP - 1) / p.TP;
+    p.st_t = y_true_stride;
+    p.st_p = y_pred_stride;
+    p.hm = L->hm;
+    p.wch = use_weights ? L->Ct - 1 : -1;
+    p.inv_hm = 1.0f / (float)L->hm;
+    p.fa = L->focal_a;
+    p.fb = L->focal_b;
+    p.a_is2 = (L->focal_a == 2.0f);
+    p.b_is4 = (L->focal_b == 4.0f);
+    p.n_fields = L->n_fields;
+    for (int f = 0; f < L->n_fields; ++f) {
+        p.f_off[f] = L->field_off[f];
+        p.f_size[f] = L->field_size[f];
+        p.f_kind[f] = L->field_kind[f];
+    }
+    p.use_bulk = cvm_aligned16(y_true) && cvm_aligned16(y_pred);
+    p.block_partials = static_cast<double*>(ws);
+
+    const int grid = loss_grid(p.n_spans, smem);
+    CVM_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    loss_fwd_kernel<<<grid, kThreads, smem, st>>>(p);
+    CVM_CHECK_LAUNCH("loss_fwd_kernel");
+    loss_reduce_kernel<<<1, 256, 0, st>>>(p.block_partials, grid, partials);
+    CVM_CHECK_LAUNCH("loss_reduce_kernel");
+    return CVM_OK;
+}
+
+extern "C" int cvm_loss_finalize(const cvm_layout* L, const double* partials, float* out, void* stream) {
+    CVM_CHECK_ARG(L && partials && out, "NULL pointer argument");
+    CVM_CHECK_ARG(L->n_fields >= 0 && L->n_fields <= CVM_MAX_FIELDS, "n_fields=%d", L->n_fields);
+    FinalizeParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.n_fields = L->n_fields;
+    for (int f = 0; f < L->n_fields; ++f) {
+        fp.f_post[f] = L->field_post[f];
+        fp.f_weight[f] = L->field_weight[f];
+    }
+    loss_finalize_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partials, out, fp);
+    CVM_CHECK_LAUNCH("loss_finalize_kernel");
+    return CVM_OK;
+}
+
+// =====================================================================================================================
+// Backward: grad_pred[n_pixels, Cp] = upstream * d(total)/d(y_pred)   (TF autograd through loss.py in the reference)
+// Same streaming structure as the forward; the gradient span is built in shared memory (zeros + heatmap terms + the few
+// regression terms at peak pixels) and leaves with one bulk async store (shared -> global) per span.
+// =====================================================================================================================
+namespace {
+
+struct BwdParams {
+    LossParams fwd;                 // tensors, strides, fields (block_partials unused)
+    const double* partials;         // globally reduced [P, N, n_pos, n_obj, field sums]
+    const float* upstream;          // device scalar or nullptr
+    float* grad;                    // [n_pixels, Cp]
+    int Cp;
+    int f_post[CVM_MAX_FIELDS];
+    float f_weight[CVM_MAX_FIELDS];
+    int grad_bulk;
+};
+
+__device__ __forceinline__ float dpow(float x, float a, int is2) {  // d/dx x^a
+    return is2 ? 2.0f * x : a * powf(x, a - 1.0f);
+}
+
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kThreads) loss_bwd_kernel(const BwdParams bp) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full_bar[kStages];
+    __shared__ float s_fscale[CVM_MAX_FIELDS];
+    __shared__ float s_focal_scale;
+
+    const LossParams& p = bp.fwd;
+    float* const ring = reinterpret_cast<float*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int TP = p.TP, Cp = bp.Cp;
+    const size_t t_floats = (size_t)TP * p.st_t;
+    const size_t stage_floats = (size_t)TP * (p.st_t + p.st_p);
+    float* const gbuf = ring + (size_t)kStages * stage_floats;  // 2 x [TP*Cp]
+    const size_t g_floats = (size_t)TP * Cp;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
+        mbar_fence_init();
+        const double up = bp.upstream ? (double)*bp.upstream : 1.0;
+        const double n = bp.partials[2], nobj = bp.partials[3];
+        s_focal_scale = (float)(n > 0.0 ? up / n : up);                                  // loss.py:59
+        for (int f = 0; f < p.n_fields; ++f) {
+            double sc = up * (double)bp.f_weight[f] * (nobj > 0.0 ? 1.0 / nobj : 1.0);    // loss.py:130,140-153
+            if (bp.f_post[f] == CVM_POST_ORIENT) {                                        // loss.py:98
+                const double v = nobj > 0.0 ? bp.partials[4 + f] / nobj : bp.partials[4 + f];
+                sc *= (0.99 * sin(2.0 * v)) / sqrt(1.0 - 0.99 * cos(2.0 * v)) + 0.1 * v;
+            }
+            s_fscale[f] = (float)sc;
+        }
+    }
+    __syncthreads();
+
+    auto span_pixels = [&](long long span) -> int {
+        const long long left = p.n_pixels - span * TP;
+        return left < TP ? (int)left : TP;
+    };
+    auto span_is_bulk = [&](long long span) -> bool { return p.use_bulk && span_pixels(span) == TP; };
+    auto load_span = [&](long long span, int s) {
+        float* dst_t = ring + (size_t)s * stage_floats;
+        float* dst_p = dst_t + t_floats;
+        const float* src_t = p.yt + span * (long long)TP * p.st_t;
+        const float* src_p = p.yp + span * (long long)TP * p.st_p;
+        if (span_is_bulk(span)) {
+            if (tid == 0) {
+                const uint32_t bt = (uint32_t)(t_floats * 4), bq = (uint32_t)((size_t)TP * p.st_p * 4);
+                mbar_arrive_expect_tx(&full_bar[s], bt + bq);
+                bulk_g2s(dst_t, src_t, bt, &full_bar[s]);
+                bulk_g2s(dst_p, src_p, bq, &full_bar[s]);
+            }
+        } else {
+            const int np = span_pixels(span);
+            for (int i = tid; i < np * p.st_t; i += kThreads) dst_t[i] = src_t[i];
+            for (int i = tid; i < np * p.st_p; i += kThreads) dst_p[i] = src_p[i];
+        }
+    };
+
+    const long long gstride = gridDim.x;
+    for (int s = 0; s < kStages; ++s) {
+        const long long span = blockIdx.x + (long long)s * gstride;
+        if (span < p.n_spans) load_span(span, s);
+    }
+
+    const int hm = p.hm, st_t = p.st_t, st_p = p.st_p, wch = p.wch;
+    const float fscale = s_focal_scale;
+    uint32_t phase_bits = 0;
+
+    for (int it = 0;; ++it) {
+        const long long span = blockIdx.x + (long long)it * gstride;
+        if (span >= p.n_spans) break;
+        const int s = it % kStages;
+        float* const G = gbuf + (size_t)(it & 1) * g_floats;
+        // the bulk store issued two iterations ago must have finished READING this gradient buffer
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (span_is_bulk(span)) {
+            mbar_wait(&full_bar[s], (phase_bits >> s) & 1u);
+            phase_bits ^= (1u << s);
+        }
+        __syncthreads();
+        const int np = span_pixels(span);
+        for (int i = tid; i < np * Cp; i += kThreads) G[i] = 0.f;
+        __syncthreads();
+
+        const float* __restrict__ T = ring + (size_t)s * stage_floats;
+        const float* __restrict__ Q = T + t_floats;
+        const int ne = np * hm;
+        for (int j = tid; j < ne; j += kThreads) {
+            int px, c;
+            if (hm == 1) {
+                px = j;
+                c = 0;
+            } else {
+                px = __float2int_rz(((float)j + 0.5f) * p.inv_hm);
+                c = j - px * hm;
+            }
+            const float y = T[px * st_t + c];
+            const float q = Q[px * st_p + c];
+            const float w = wch >= 0 ? T[px * st_t + wch] : 1.0f;
+            float g = 0.f;
+            if (y < 1.0f) {
+                const float u = 1.0f - q;
+                const float l = logf(fminf(fmaxf(u, 0.01f), 0.99f));
+                const float dl = (u >= 0.01f && u <= 0.99f) ? -1.0f / u : 0.0f;   // clip_by_value passes grad inside [min,max]
+                g = -pow_b(1.0f - y, p) * (dpow(q, p.fa, p.a_is2) * l + pow_a(q, p) * dl);
+            } else if (y == 1.0f) {
+                const float u = 1.0f - q;
+                const float l = logf(fminf(fmaxf(q, 0.01f), 0.99f));
+                const float dl = (q >= 0.01f && q <= 0.99f) ? 1.0f / q : 0.0f;
+                g = dpow(u, p.fa, p.a_is2) * l - pow_a(u, p) * dl;
+                bool owner = true;
+                for (int c2 = 0; c2 < c; ++c2) owner = owner && !(T[px * st_t + c2] == 1.0f);
+                if (owner) {
+                    for (int f = 0; f < p.n_fields; ++f) {
+                        const float* t = T + px * st_t + p.f_off[f];
+                        const float* qq = Q + px * st_p + p.f_off[f];
+                        float* gg = G + px * Cp + p.f_off[f];
+                        const int size = p.f_size[f], kind = p.f_kind[f];
+                        const float sc = s_fscale[f];
+                        if (kind == CVM_KIND_CE) {
+                            float mx = qq[0];
+                            for (int k = 1; k < size; ++k) mx = fmaxf(mx, qq[k]);
+                            float se = 0.f, st = 0.f;
+                            for (int k = 0; k < size; ++k) {
+                                se += expf(qq[k] - mx);
+                                st += t[k];
+                            }
+                            const float lse = mx + logf(se);
+                            float ce = 0.f;
+                            for (int k = 0; k < size; ++k) ce += t[k] * (lse - qq[k]);
+                            const float sg = ce > 0.f ? 1.f : (ce < 0.f ? -1.f : 0.f);
+                            for (int k = 0; k < size; ++k) gg[k] += sc * sg * (st * expf(qq[k] - lse) - t[k]);
+                        } else {
+                            for (int k = 0; k < size; ++k) {
+                                const float d = t[k] - qq[k];
+                                float dv;
+                                if (kind == CVM_KIND_MSE)
+                                    dv = -2.0f * d;
+                                else if (kind == CVM_KIND_MAE)
+                                    dv = d > 0.f ? -1.f : (d < 0.f ? 1.f : 0.f);
+                                else {
+                                    const float den = fmaxf(fabsf(t[k]), 1.0f);
+                                    dv = (d > 0.f ? -1.f : (d < 0.f ? 1.f : 0.f)) / den;
+                                }
+                                gg[k] += sc * dv;
+                            }
+                        }
+                    }
+                }
+            }
+            G[px * Cp + c] = g * w * fscale;
+        }
+        __syncthreads();
+        float* dst = bp.grad + span * (long long)TP * Cp;
+        if (bp.grad_bulk && np == TP) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async-proxy read
+            __syncthreads();
+            if (tid == 0) bulk_s2g(dst, G, (uint32_t)(g_floats * 4));
+        } else {
+            for (int i = tid; i < np * Cp; i += kThreads) dst[i] = G[i];
+            __syncthreads();
+        }
+        const long long next = span + (long long)kStages * gstride;
+        if (next < p.n_spans) load_span(next, s);
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the last store's read
+}
+
+}  // namespace
+
+extern "C" int cvm_loss_bwd(const cvm_layout* L, const float* y_true, int y_true_stride, const float* y_pred,
+                            int y_pred_stride, long long n_pixels, const double* partials, const float* upstream,
+                            float* grad_pred, void* stream) {
+    int rc = check_layout_for_loss(L, y_true_stride, y_pred_stride);
+    if (rc != CVM_OK) return rc;
+    CVM_CHECK_ARG(y_true && y_pred && partials && grad_pred, "NULL pointer argument");
+    CVM_CHECK_ARG(n_pixels >= 0, "n_pixels < 0");
+    if (n_pixels == 0) return CVM_OK;
+    BwdParams bp;
+    memset(&bp, 0, sizeof(bp));
+    LossParams& p = bp.fwd;
+    // ring (3 stages) + two gradient buffers within ~100 KB
+    int TP = 256;
+    const int per_px = kStages * (y_true_stride + y_pred_stride) + 2 * L->Cp;
+    while (TP > 16 && (size_t)TP * per_px * 4 > 100 * 1024) TP >>= 1;
+    const size_t smem = (size_t)TP * per_px * 4;
+    p.TP = TP;
+    p.yt = y_true;
+    p.yp = y_pred;
+    p.n_pixels = n_pixels;
+    p.n_spans = (n_pixels + TP - 1) / TP;
+    p.st_t = y_true_stride;
+    p.st_p = y_pred_stride;
+    p.hm = L->hm;
+    p.wch = L->Ct - 1;
+    p.inv_hm = 1.0f / (float)L->hm;
+    p.fa = L->focal_a;
+    p.fb = L->focal_b;
+    p.a_is2 = (L->focal_a == 2.0f);
+    p.b_is4 = (L->focal_b == 4.0f);
+    p.n_fields = L->n_fields;
+    for (int f = 0; f < L->n_fields; ++f) {
+        p.f_off[f] = L->field_off[f];
+        p.f_size[f] = L->field_size[f];
+        p.f_kind[f] = L->field_kind[f];
+        bp.f_post[f] = L->field_post[f];
+        bp.f_weight[f] = L->field_weight[f];
+    }
+    p.use_bulk = cvm_aligned16(y_true) && cvm_aligned16(y_pred);
+    bp.partials = partials;
+    bp.upstream = upstream;
+    bp.grad = grad_pred;
+    bp.Cp = L->Cp;
+    bp.grad_bulk = cvm_aligned16(grad_pred);
+    const int grid = loss_grid(p.n_spans, smem);
+    CVM_CHECK_CUDA(cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    loss_bwd_kernel<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(bp);
+    CVM_CHECK_LAUNCH("loss_bwd_kernel");
+    return CVM_OK;
+}

@@ -1,0 +1,3 @@
+from .params import CentertrackerParams
+from .processor import CenterTrackerProcess
+from .loss import CentertrackerLoss

@@ -1,0 +1,235 @@
+"""Tensor-level entry points: torch CUDA tensors in/out, all math inside libcvmhot.so (C ABI, include/cvmhot.h).
+
+torch is only used for device memory and streams.  Every function enqueues on torch's current CUDA stream and never
+synchronises.  There is no CPU path: passing a CPU tensor raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .layout import Layout
+
+OBJ_DTYPE = np.dtype([("x", "<f8"), ("y", "<f8"), ("w", "<f8"), ("h", "<f8"), ("cx", "<i4"), ("cy", "<i4"),
+                      ("cls", "<i4"), ("flags", "<i4"), ("peak", "<f4"), ("track", "<f4", (2,)), ("_pad", "<f4")])
+BOX_DTYPE = np.dtype([("x", "<f8"), ("y", "<f8"), ("w", "<f8"), ("h", "<f8")])
+ROI_DTYPE = np.dtype([("inv_scale", "<f4"), ("off_left", "<f4"), ("off_top", "<f4"), ("_pad", "<f4")])
+assert OBJ_DTYPE.itemsize == 64 and BOX_DTYPE.itemsize == 32 and ROI_DTYPE.itemsize == 16
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _need_cuda(t, name, dtype=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.CvmError(f"{name} must be a CUDA tensor (there is no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.CvmError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def _pixel_strided(t, name):
+    """Accept [..., C] tensors that are contiguous up to a channel slice; return the per-pixel stride in floats."""
+    _need_cuda(t, name, torch.float32)
+    if t.dim() < 2 or t.stride(-1) != 1:
+        raise _lib.CvmError(f"{name}: channel dimension must be innermost and dense")
+    st = t.stride(-2)
+    expect = st
+    for d in range(t.dim() - 2, -1, -1):
+        if t.size(d) != 1 and t.stride(d) != expect:
+            raise _lib.CvmError(f"{name}: only NHWC-contiguous tensors (or channel slices of them) are supported")
+        expect *= t.size(d)
+    return int(st)
+
+
+def to_device_records(arr, dtype, device):
+    """numpy structured array -> uint8 CUDA tensor holding the same bytes."""
+    arr = np.ascontiguousarray(arr, dtype=dtype)
+    if arr.size == 0:
+        return torch.zeros(dtype.itemsize, dtype=torch.uint8, device=device)   # never dereferenced
+    return torch.from_numpy(arr.view(np.uint8).reshape(-1)).to(device, non_blocking=True)
+
+
+def make_rois(rois, device):
+    """rois: iterable of (scale, offset_left, offset_top) per image -> device records (inv_scale rounded like NumPy does)."""
+    a = np.zeros(len(rois), dtype=ROI_DTYPE)
+    for i, (scale, ol, ot) in enumerate(rois):
+        a[i]["inv_scale"] = np.float32(1.0 / scale)
+        a[i]["off_left"] = np.float32(ol)
+        a[i]["off_top"] = np.float32(ot)
+    return to_device_records(a, ROI_DTYPE, device)
+
+
+_ws_cache = {}
+
+
+def _workspace(device, nbytes, tag):
+    # one scratch buffer per (device, stream, purpose): concurrent callers on different streams never share it
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream, tag)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+# ---- render ----------------------------------------------------------------------------------------------------------
+def render_gt(layout: Layout, objs_dev, obj_offsets_dev, B, ignore_dev=None, ign_offsets_dev=None, out=None):
+    """y_true [B,H,W,Ct] from device object records (see pack in models/centernet/processor.py)."""
+    _need_cuda(objs_dev, "objs")
+    _need_cuda(obj_offsets_dev, "obj_offsets", torch.int32)
+    if out is None:
+        out = torch.empty((B, layout.H, layout.W, layout.Ct), dtype=torch.float32, device=objs_dev.device)
+    _need_cuda(out, "out", torch.float32)
+    if tuple(out.shape) != (B, layout.H, layout.W, layout.Ct) or not out.is_contiguous():
+        raise _lib.CvmError("out must be a contiguous [B,H,W,Ct] tensor")
+    s = layout.c_struct()
+    rc = _lib.lib().cvm_render_gt(C.byref(s), _ptr(objs_dev), _ptr(obj_offsets_dev), _ptr(ignore_dev),
+                                  _ptr(ign_offsets_dev), B, _ptr(out), _stream())
+    _lib.check(rc, "cvm_render_gt")
+    return out
+
+
+def render_prev_heatmap(layout: Layout, objs_dev, obj_offsets_dev, B, out=None):
+    _need_cuda(objs_dev, "objs")
+    _need_cuda(obj_offsets_dev, "obj_offsets", torch.int32)
+    if out is None:
+        out = torch.empty((B, layout.H, layout.W, 1), dtype=torch.float32, device=objs_dev.device)
+    s = layout.c_struct()
+    rc = _lib.lib().cvm_render_prev_hm(C.byref(s), _ptr(objs_dev), _ptr(obj_offsets_dev), B, _ptr(out), _stream())
+    _lib.check(rc, "cvm_render_prev_hm")
+    return out
+
+
+def fill_heatmap_inplace(objs_dev, n_obj, heat, weights, H, W, R, alpha):
+    """max/min-combine records into existing planes: heat [H,W,C] (channel 0 of the given view) and weights [H,W] or None."""
+    _need_cuda(heat, "heat", torch.float32)
+    hs = int(heat.stride(-2)) if heat.dim() == 3 else 1
+    rc = _lib.lib().cvm_fill_heatmap_inplace(_ptr(objs_dev), int(n_obj), _ptr(heat), hs, _ptr(weights), int(H), int(W),
+                                             float(R), float(alpha), _stream())
+    _lib.check(rc, "cvm_fill_heatmap_inplace")
+
+
+# ---- loss ------------------------------------------------------------------------------------------------------------
+def _n_pixels(t):
+    n = 1
+    for d in t.shape[:-1]:
+        n *= int(d)
+    return n
+
+
+def loss_partials(layout: Layout, y_true, y_pred, use_weights=True, out=None):
+    """One streaming pass -> fp64[16] device vector [P, N, n_pos, n_obj, field sums...] (sum it across GPUs, then finalize)."""
+    st_t = _pixel_strided(y_true, "y_true")
+    st_p = _pixel_strided(y_pred, "y_pred")
+    n = _n_pixels(y_true)
+    if _n_pixels(y_pred) != n:
+        raise _lib.CvmError("y_true and y_pred must cover the same pixels")
+    if out is None:
+        out = torch.empty(_lib.CVM_NPART, dtype=torch.float64, device=y_true.device)
+    s = layout.c_struct()
+    nbytes = _lib.lib().cvm_loss_workspace_bytes(C.byref(s), n)
+    ws = _workspace(y_true.device, nbytes, "loss")
+    rc = _lib.lib().cvm_loss_fwd(C.byref(s), _ptr(y_true), st_t, _ptr(y_pred), st_p, n, int(bool(use_weights)),
+                                 _ptr(out), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "cvm_loss_fwd")
+    return out
+
+
+def loss_finalize(layout: Layout, partials, out=None):
+    """-> float32 device vector [total, focal, field_0, ...] (fields normalised, post-transformed, unweighted)."""
+    _need_cuda(partials, "partials", torch.float64)
+    if out is None:
+        out = torch.zeros(2 + _lib.CVM_MAX_FIELDS, dtype=torch.float32, device=partials.device)
+    s = layout.c_struct()
+    rc = _lib.lib().cvm_loss_finalize(C.byref(s), _ptr(partials), _ptr(out), _stream())
+    _lib.check(rc, "cvm_loss_finalize")
+    return out
+
+
+def loss_backward(layout: Layout, y_true, y_pred, partials, upstream=None, out=None):
+    """grad wrt y_pred[..., :Cp] as a contiguous [n_pixels, Cp] tensor; `partials` must be the globally reduced vector."""
+    st_t = _pixel_strided(y_true, "y_true")
+    st_p = _pixel_strided(y_pred, "y_pred")
+    n = _n_pixels(y_true)
+    if out is None:
+        out = torch.empty(tuple(y_pred.shape[:-1]) + (layout.Cp,), dtype=torch.float32, device=y_pred.device)
+    if upstream is not None:
+        _need_cuda(upstream, "upstream", torch.float32)
+    s = layout.c_struct()
+    rc = _lib.lib().cvm_loss_bwd(C.byref(s), _ptr(y_true), st_t, _ptr(y_pred), st_p, n, _ptr(partials), _ptr(upstream),
+                                 _ptr(out), _stream())
+    _lib.check(rc, "cvm_loss_bwd")
+    return out
+
+
+# ---- decode ----------------------------------------------------------------------------------------------------------
+def decode_topk(layout: Layout, y_pred, K=100, rois_dev=None, want_track=None):
+    """Canonical CenterNet decode -> dict(scores[B,K], cls[B,K] i32, flat[B,K] i64, centers[B,K,2], boxes[B,K,4], track[B,K,2])."""
+    st = _pixel_strided(y_pred, "y_pred")
+    if y_pred.dim() != 4 or y_pred.shape[1] != layout.H or y_pred.shape[2] != layout.W:
+        raise _lib.CvmError("y_pred must be [B,H,W,C] with the layout's H,W")
+    B = int(y_pred.shape[0])
+    dev = y_pred.device
+    if want_track is None:
+        want_track = layout.off_track >= 0
+    out = dict(scores=torch.empty((B, K), dtype=torch.float32, device=dev),
+               cls=torch.empty((B, K), dtype=torch.int32, device=dev),
+               flat=torch.empty((B, K), dtype=torch.int64, device=dev),
+               centers=torch.empty((B, K, 2), dtype=torch.float32, device=dev),
+               boxes=torch.empty((B, K, 4), dtype=torch.float32, device=dev),
+               track=torch.empty((B, K, 2), dtype=torch.float32, device=dev) if want_track else None)
+    s = layout.c_struct()
+    nbytes = _lib.lib().cvm_decode_topk_workspace_bytes(C.byref(s), st, B, K)
+    if nbytes == 0 and B > 0:
+        raise _lib.CvmError("cvm_decode_topk: unsupported shape: " + _lib.lib().cvm_last_error().decode())
+    ws = _workspace(dev, nbytes, "decode")
+    rc = _lib.lib().cvm_decode_topk(C.byref(s), _ptr(y_pred), st, B, K, _ptr(rois_dev), _ptr(out["scores"]),
+                                    _ptr(out["cls"]), _ptr(out["flat"]), _ptr(out["centers"]), _ptr(out["boxes"]),
+                                    _ptr(out["track"]), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "cvm_decode_topk")
+    return out
+
+
+def decode_window9(layout: Layout, y_pred, min_conf=0.25, rois_dev=None, max_out=256, window=9):
+    """The reference's process_2d_output on a batch -> dict(counts[B], cls, pix, scores, centers, boxes) in scan order."""
+    st = _pixel_strided(y_pred, "y_pred")
+    B = int(y_pred.shape[0])
+    dev = y_pred.device
+    out = dict(counts=torch.zeros(B, dtype=torch.int32, device=dev),
+               cls=torch.zeros((B, max_out), dtype=torch.int32, device=dev),
+               pix=torch.zeros((B, max_out), dtype=torch.int32, device=dev),
+               scores=torch.zeros((B, max_out), dtype=torch.float32, device=dev),
+               centers=torch.zeros((B, max_out, 2), dtype=torch.float32, device=dev),
+               boxes=torch.zeros((B, max_out, 4), dtype=torch.float32, device=dev))
+    s = layout.c_struct()
+    ws = _workspace(dev, _lib.lib().cvm_decode_window9_workspace_bytes(C.byref(s), B), "window9")
+    rc = _lib.lib().cvm_decode_window9(C.byref(s), _ptr(y_pred), st, B, window, float(min_conf), _ptr(rois_dev), max_out,
+                                       _ptr(out["counts"]), _ptr(out["cls"]), _ptr(out["pix"]), _ptr(out["scores"]),
+                                       _ptr(out["centers"]), _ptr(out["boxes"]), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "cvm_decode_window9")
+    return out
+
+
+# ---- semseg argmax ---------------------------------------------------------------------------------------------------
+def semseg_argmax(x, off, n_cls, lut_bgr=None, threshold=None, use_weight=False, apply_softmax=True):
+    """x [...,C] float32 CUDA. lut_bgr None -> uint8 class ids [...]; else uint8 BGR [...,3] with to_3channel semantics."""
+    st = _pixel_strided(x, "x")
+    n = _n_pixels(x)
+    if lut_bgr is None:
+        out = torch.empty(tuple(x.shape[:-1]), dtype=torch.uint8, device=x.device)
+        mode = 0
+    else:
+        _need_cuda(lut_bgr, "lut_bgr", torch.uint8)
+        out = torch.empty(tuple(x.shape[:-1]) + (3,), dtype=torch.uint8, device=x.device)
+        mode = 1
+    thr = float("nan") if threshold is None else float(threshold)
+    rc = _lib.lib().cvm_semseg_argmax(_ptr(x), n, st, int(off), int(n_cls), mode, int(bool(apply_softmax)),
+                                      int(bool(use_weight)), thr, _ptr(lut_bgr), _ptr(out), _stream())
+    _lib.check(rc, "cvm_semseg_argmax")
+    return out

@@ -1,0 +1,158 @@
+"""GPU parity: cvm_decode_topk (canonical CenterNet decode) and cvm_decode_window9 (the reference's process_2d_output)
+through the C ABI.  Bar (north_star): top-K flat indices, class ids and scores BIT-EXACT under the lowest-flat-index
+tie-break; boxes/centres are fp32 op-for-op like NumPy, so they are compared exactly too."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import decode_np
+from oracle.layout import make_layout
+
+pytestmark = pytest.mark.gpu
+
+
+def _params(nb, per_class, H, W, track=False):
+    from cvmhot.models.centernet import CenternetParams
+    from cvmhot.models.centertracker import CentertrackerParams
+    p = (CentertrackerParams if track else CenternetParams)(nb, per_class)
+    p.INPUT_HEIGHT, p.INPUT_WIDTH = H * p.R, W * p.R
+    return p
+
+
+def _check_topk(out, ref, K_eff):
+    for k in ("scores", "cls", "flat", "centers", "boxes"):
+        got = out[k].cpu().numpy()[:, :K_eff]
+        assert np.array_equal(got, ref[k]), k
+
+
+@pytest.mark.parametrize("H,W,K_cls,track,B,K", [(128, 384, 10, False, 4, 100), (128, 384, 10, True, 3, 100),
+                                                 (37, 53, 7, False, 5, 100), (64, 1000, 4, False, 2, 50),
+                                                 (9, 11, 1, False, 2, 100), (20, 20, 3, False, 3, 7)])
+def test_topk_vs_oracle(cuda, H, W, K_cls, track, B, K):
+    from cvmhot.models.centernet.post_processing import decode_topk
+    from cvmhot.common.utils import Roi
+    Lo = make_layout(H, W, K_cls, "N", track=track)
+    data = synth.make_batch(Lo, 4, B, track=track)
+    yp = data["y_pred"]
+    rois = [(1.0, 0, 0), (0.25, -5, -3), (0.5, 3, 7), (2.0, 0, 1), (1.0, 0, 0)][:B]
+    ref = decode_np.decode_topk(Lo, yp, K, rois)
+    roi_objs = []
+    for s, l, t in rois:
+        r = Roi(); r.scale, r.offset_left, r.offset_top = s, l, t
+        roi_objs.append(r)
+    out = decode_topk(torch.from_numpy(yp).to(cuda), _params(K_cls, True, H, W, track), K=K, rois=roi_objs)
+    K_eff = ref["scores"].shape[1]
+    _check_topk(out, ref, K_eff)
+    if track:
+        assert np.array_equal(out["track"].cpu().numpy()[:, :K_eff], ref["track"])
+    if K_eff < K:      # fewer elements than K: the rest is marked invalid
+        assert (out["flat"].cpu().numpy()[:, K_eff:] == -1).all() and (out["cls"].cpu().numpy()[:, K_eff:] == -1).all()
+
+
+def test_topk_ties_plateaus_and_sparse_maps(cuda):
+    from cvmhot.models.centernet.post_processing import decode_topk
+    H, W, C = 48, 64, 6
+    Lo = make_layout(H, W, C, "N")
+    rng = np.random.default_rng(11)
+    yp = np.zeros((5, H, W, Lo.Cp), np.float32)
+    yp[..., Lo.hm:] = rng.uniform(0, 50, (5, H, W, Lo.Cp - Lo.hm))
+    # 0: only 7 positive peaks -> tail of score-0 entries in flat order (some of the first flats are peaks themselves)
+    for (y, x, c, v) in [(0, 0, 0, .5), (0, 0, 2, .7), (0, 1, 1, .7), (10, 10, 3, .2), (47, 63, 5, .9), (20, 5, 0, .9), (0, 3, 4, .1)]:
+        yp[0, y, x, c] = v
+    # 1: constant map -> everything is a plateau peak with equal score: the first K flat indices win
+    yp[1, ..., :C] = 0.3
+    # 2: all zeros -> no positive peak at all
+    # 3: many exact duplicates of a few values (heavy ties across channels and rows)
+    yp[3, ..., :C] = rng.choice(np.array([0.1, 0.2, 0.7, 0.9], np.float32), size=(H, W, C))
+    # 4: monotone ramp (every row has exactly one peak per channel at the right border) + a negative region
+    yp[4, ..., :C] = (np.arange(W, dtype=np.float32)[None, :, None] / W + 0.001 * np.arange(C, dtype=np.float32)) - 0.2
+    ref = decode_np.decode_topk(Lo, yp, 100)
+    out = decode_topk(torch.from_numpy(yp).to(cuda), _params(C, True, H, W), K=100)
+    _check_topk(out, ref, 100)
+    assert (ref["scores"][2] == 0).all() and np.array_equal(ref["flat"][2], np.arange(100))
+    assert np.array_equal(ref["flat"][1], np.arange(100))
+
+
+def test_topk_compaction_stress(cuda):
+    """Dense, slowly rising maps force many threshold raises/compactions inside one stripe."""
+    from cvmhot.models.centernet.post_processing import decode_topk
+    H, W, C = 128, 384, 10
+    Lo = make_layout(H, W, C, "N")
+    rng = np.random.default_rng(12)
+    yp = np.zeros((2, H, W, Lo.Cp), np.float32)
+    base = rng.uniform(0.01, 0.5, (2, H, W, C)).astype(np.float32)
+    ramp = (np.arange(H, dtype=np.float32) / H * 0.45)[None, :, None, None]      # later rows score higher
+    yp[..., :C] = base + ramp
+    yp[1, ..., :C] = yp[1, ::-1, :, :C]                                             # and the reverse
+    ref = decode_np.decode_topk(Lo, yp, 100)
+    out = decode_topk(torch.from_numpy(yp).to(cuda), _params(C, True, H, W), K=100)
+    _check_topk(out, ref, 100)
+
+
+def test_topk_properties_full_size(cuda):
+    """BASELINE config 2 shape (B=256 is sampled down to 64 to keep the host reference affordable):
+    size-independent properties + spot parity on a few images."""
+    from cvmhot.models.centernet.post_processing import decode_topk
+    H, W, C, B = 128, 384, 10, 64
+    Lo = make_layout(H, W, C, "N")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    yp = torch.empty((B, H, W, Lo.Cp), device=cuda)
+    yp[..., :C] = torch.sigmoid(torch.randn((B, H, W, C), device=cuda, generator=g) * 1.5 - 4.0)
+    yp[..., C:] = torch.rand((B, H, W, Lo.Cp - C), device=cuda, generator=g) * 40
+    out = decode_topk(yp, _params(C, True, H, W), K=100)
+    s, f, c = out["scores"], out["flat"], out["cls"]
+    assert bool((s[:, :-1] >= s[:, 1:]).all())                                     # sorted by score
+    tie = s[:, :-1] == s[:, 1:]
+    assert bool((f[:, :-1][tie] < f[:, 1:][tie]).all())                            # ties by ascending flat index
+    assert bool((c.long() == f % C).all())
+    hm = yp[..., :C].reshape(B, -1)
+    assert bool((hm.gather(1, f) == s).all())                                      # scores are the map values at flat
+    mp = torch.nn.functional.max_pool2d(yp[..., :C].permute(0, 3, 1, 2), 3, 1, 1).permute(0, 2, 3, 1).reshape(B, -1)
+    assert bool((mp.gather(1, f) == s).all())                                      # every winner is a 3x3 maximum
+    # nothing better was missed: the K-th score bounds every other peak
+    peaks = torch.where(hm == mp, hm, torch.zeros_like(hm))
+    peaks.scatter_(1, f, 0.0)
+    assert bool((peaks.max(dim=1).values <= s[:, -1]).all())
+    out2 = decode_topk(yp, _params(C, True, H, W), K=100)                          # idempotent / deterministic
+    assert all(torch.equal(out[k], out2[k]) for k in ("scores", "flat", "cls", "boxes"))
+    ref = decode_np.decode_topk(Lo, yp[:3].cpu().numpy(), 100)
+    _check_topk({k: v[:3] for k, v in out.items() if v is not None}, ref, 100)
+
+
+def test_window9_vs_real_golden(cuda, golden_dir):
+    from cvmhot.models.centernet import CenternetParams, process_2d_output
+    from cvmhot.common.utils import Roi
+    g = np.load(os.path.join(golden_dir, "decode_r.npz"))
+    p = CenternetParams(int(g["nb_classes"]))
+    roi = Roi(); roi.scale, roi.offset_left, roi.offset_top = [float(v) for v in g["roi"]]
+    objs = process_2d_output(g["mask"], roi, p, float(g["min_conf"]))
+    assert [o["cls_idx"] for o in objs] == list(g["cls"])
+    assert np.array_equal(np.array([o["center"] for o in objs], np.float32), g["center"])
+    assert np.array_equal(np.array([o["fullbox"] for o in objs], np.float32), g["fullbox"])
+
+
+@pytest.mark.parametrize("H,W,nb", [(128, 384, 10), (9, 11, 3), (40, 57, 6)])
+def test_window9_vs_oracle(cuda, H, W, nb):
+    from cvmhot import ops
+    from cvmhot.layout import layout_from_params
+    Lo = make_layout(H, W, nb, "R")
+    B = 3
+    data = synth.make_batch(Lo, 6, B)
+    yp = data["y_pred"]
+    yp[..., 0] = np.maximum(yp[..., 0], (np.random.default_rng(1).uniform(0, 1, (B, H, W)) > 0.97) * 0.6).astype(np.float32)
+    rois = [(0.25, -5, -3), (1.0, 0, 0), (0.5, 2, 9)]
+    out = ops.decode_window9(layout_from_params(_params(nb, False, H, W)), torch.from_numpy(yp).to(cuda), 0.25,
+                             ops.make_rois(rois, cuda), max_out=400)
+    for b in range(B):
+        ref = decode_np.decode_window9(Lo, yp[b], rois[b], 0.25)
+        n = int(out["counts"][b])
+        assert n == len(ref)
+        assert list(out["pix"][b, :n].cpu().numpy()) == [o["y"] * W + o["x"] for o in ref]      # scan order
+        assert list(out["cls"][b, :n].cpu().numpy()) == [o["cls_idx"] for o in ref]
+        if n:
+            assert np.array_equal(out["centers"][b, :n].cpu().numpy(), np.array([o["center"] for o in ref], np.float32))
+            assert np.array_equal(out["boxes"][b, :n].cpu().numpy(), np.array([o["fullbox"] for o in ref], np.float32))
+            assert np.array_equal(out["scores"][b, :n].cpu().numpy(), np.array([o["score"] for o in ref], np.float32))
