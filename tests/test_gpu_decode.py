@@ -145,7 +145,7 @@ def test_window9_vs_oracle(cuda, H, W, nb):
     yp[..., 0] = np.maximum(yp[..., 0], (np.random.default_rng(1).uniform(0, 1, (B, H, W)) > 0.97) * 0.6).astype(np.float32)
     rois = [(0.25, -5, -3), (1.0, 0, 0), (0.5, 2, 9)]
     out = ops.decode_window9(layout_from_params(_params(nb, False, H, W)), torch.from_numpy(yp).to(cuda), 0.25,
-                             ops.make_rois(rois, cuda), max_out=400)
+                             ops.make_rois(rois, cuda), max_out=2000)
     for b in range(B):
         ref = decode_np.decode_window9(Lo, yp[b], rois[b], 0.25)
         n = int(out["counts"][b])
