@@ -111,7 +111,103 @@ __device__ void select_topk(unsigned long long* keys, int n, int K, unsigned int
 
 __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
 
+// Everything the per-row step needs that is not per-thread register state.
+struct StreamCtx {
+    float* ring;
+    unsigned long long* cand;
+    unsigned long long* keep;
+    uint64_t* full_bar;
+    unsigned int* hist;
+    int* s_misc;
+    int* s_count;
+    unsigned long long* s_thr;
+    const float* gsrc;        // global address of (row ra-1, pixel px_lo, channel 0) (virtual when ra == 0)
+    long long row_floats_g;   // W * stride
+    int row_floats;           // (px_hi - px_lo) * stride
+    int lead;                 // data of a row starts `lead` floats into its slot (16-byte granularity of the bulk copy)
+    int slot_floats, r_last, ra, rb, H, K, compact_at, bulk;
+    unsigned flat_x0, flat_row_step;
+};
+
+// global -> ring slot (row r lives in slot (r - (ra-1)) & 3): thread 0 with the bulk engine, or everybody with plain loads
+__device__ __forceinline__ void load_row(const StreamCtx& c, int r, int tid) {
+    const int i = r - (c.ra - 1), s = i & (kSlots - 1);
+    float* dst = c.ring + (size_t)s * c.slot_floats;
+    const float* src = c.gsrc + (long long)i * c.row_floats_g;       // first needed float
+    if (c.bulk) {
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)(((c.lead + c.row_floats + 3) & ~3) * 4);
+            mbar_arrive_expect_tx(&c.full_bar[s], bytes);
+            bulk_g2s(dst, src - c.lead, bytes, &c.full_bar[s]);
+        }
+    } else {
+        for (int j = tid; j < c.row_floats; j += kThreads) dst[c.lead + j] = src[j];
+    }
+}
+
+// One row step: bring row r's values/3-tap maxima into (vn, hn), test row r-1 with (hp, hc, hn, vc), release the slot.
+// SLOT (= step index mod 4) is a compile-time constant, so every shared load is [per-thread offset + uniform slot base].
+template <int SLOT>
+__device__ __forceinline__ void row_step(const StreamCtx& c, int r, int tid, const float* const (&pv)[kE],
+                                         const float* const (&pl)[kE], const float* const (&pr)[kE],
+                                         const float (&hp)[kE], const float (&hc)[kE], float (&hn)[kE],
+                                         const float (&vc)[kE], float (&vn)[kE], uint32_t& phase_bits,
+                                         unsigned long long& thr, float& thr_f, int& trigger) {
+    const bool in_img = (r >= 0 && r < c.H);
+    if (in_img) {
+        if (c.bulk) {
+            mbar_wait(&c.full_bar[SLOT], (phase_bits >> SLOT) & 1u);
+            phase_bits ^= 1u << SLOT;
+        } else {
+            __syncthreads();
+        }
+        const int so = SLOT * c.slot_floats;
+#pragma unroll
+        for (int k = 0; k < kE; ++k) {
+            const float v = pv[k][so];
+            vn[k] = v;
+            hn[k] = fmaxf(v, fmaxf(pl[k][so], pr[k][so]));
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kE; ++k) vn[k] = hn[k] = neg_inf();
+    }
+    const int yt = r - 1;  // row whose 3x3 neighbourhood is now complete
+    if (yt >= c.ra && yt < c.rb) {
+        const unsigned flat_row = (unsigned)yt * c.flat_row_step + c.flat_x0;
+#pragma unroll
+        for (int k = 0; k < kE; ++k) {
+            // peak (value equals its 3x3 max), positive, and not below the running threshold: one compare
+            if (vc[k] >= fmaxf(fmaxf(hp[k], hc[k]), fmaxf(hn[k], thr_f))) {
+                const unsigned flat = flat_row + (unsigned)(k * kThreads);
+                const unsigned long long key =
+                    ((unsigned long long)__float_as_uint(vc[k]) << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
+                if (key > thr) {
+                    const int pos = atomicAdd(c.s_count, 1);
+                    c.cand[pos] = key;
+                    trigger |= (pos >= c.compact_at);
+                }
+            }
+        }
+    }
+    // slot consumed by everyone; appends of this row are visible.  The OR of the per-thread marks is the only race-free
+    // uniform way to learn "buffer passed the mark" (fast threads may already append for the next row once they leave
+    // a plain barrier, so *s_count itself must not be sampled here).
+    const int do_compact = __syncthreads_or(trigger);
+    // refill this step's slot with the row 4 steps ahead (also after the virtual row -1 of a top stripe, whose slot is idle)
+    if (r + kSlots >= 0 && r + kSlots <= c.r_last) load_row(c, r + kSlots, tid);
+    if (do_compact) {  // every thread is in here, so *s_count is frozen
+        select_topk(c.cand, *c.s_count, c.K, c.hist, c.keep, c.s_misc, c.s_thr);
+        if (tid == 0) *c.s_count = c.K;
+        trigger = 0;
+        __syncthreads();
+        thr = *c.s_thr;
+        thr_f = __uint_as_float((unsigned)(thr >> 32));
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) decode_stream_kernel(const DecodeParams p) {
+    static_assert(kSlots == 4, "the row-step rotation below has period 4");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full_bar[kSlots];
     __shared__ unsigned int hist[256];
@@ -119,9 +215,15 @@ __global__ void __launch_bounds__(kThreads) decode_stream_kernel(const DecodePar
     __shared__ int s_count;
     __shared__ unsigned long long s_thr;
 
-    float* const ring = reinterpret_cast<float*>(smem_raw);
-    unsigned long long* const cand = reinterpret_cast<unsigned long long*>(ring + (size_t)kSlots * p.slot_floats);
-    unsigned long long* const keep = cand + p.cap;
+    StreamCtx c;
+    c.ring = reinterpret_cast<float*>(smem_raw);
+    c.cand = reinterpret_cast<unsigned long long*>(c.ring + (size_t)kSlots * p.slot_floats);
+    c.keep = c.cand + p.cap;
+    c.full_bar = full_bar;
+    c.hist = hist;
+    c.s_misc = s_misc;
+    c.s_count = &s_count;
+    c.s_thr = &s_thr;
 
     const int tid = threadIdx.x;
     int bid = blockIdx.x;
@@ -132,9 +234,28 @@ __global__ void __launch_bounds__(kThreads) decode_stream_kernel(const DecodePar
 
     const int H = p.H, W = p.W, hm = p.hm, stride = p.stride;
     const int xa = bx * p.TW, xb = min(W, xa + p.TW);
-    const int ra = sy * p.SR, rb = min(H, ra + p.SR);
     const int px_lo = max(xa - 1, 0), px_hi = min(xb + 1, W);
-    const int r_first = max(ra - 1, 0), r_last = min(rb, H - 1);
+    c.ra = sy * p.SR;
+    c.rb = min(H, c.ra + p.SR);
+    const int r_first = max(c.ra - 1, 0);
+    c.r_last = min(c.rb, H - 1);
+    c.H = H;
+    c.K = p.K;
+    c.compact_at = p.compact_at;
+    c.slot_floats = p.slot_floats;
+    c.row_floats = (px_hi - px_lo) * stride;
+    c.row_floats_g = (long long)W * stride;
+    const long long f_virtual = (((long long)b * H + (c.ra - 1)) * W + px_lo) * stride;   // may point before the tensor when ra == 0
+    c.gsrc = p.yp + f_virtual;
+    c.lead = (int)((f_virtual + (c.ra == 0 ? c.row_floats_g : 0)) & 3LL);
+    c.flat_x0 = (unsigned)(xa * hm + tid);
+    c.flat_row_step = (unsigned)(W * hm);
+    // the bulk engine needs 16-byte granules: every row of this CTA must start at the same offset mod 4 floats, and the
+    // rounded-up end of its last row must stay inside the tensor; otherwise this CTA uses plain cooperative loads
+    {
+        const long long f_hi_last = f_virtual + (long long)(c.r_last - (c.ra - 1)) * c.row_floats_g + c.row_floats;
+        c.bulk = p.use_bulk && ((c.row_floats_g & 3LL) == 0) && (((f_hi_last + 3) & ~3LL) <= p.total_floats);
+    }
     const int n_elem = (xb - xa) * hm;
 
     if (tid == 0) {
@@ -143,134 +264,58 @@ __global__ void __launch_bounds__(kThreads) decode_stream_kernel(const DecodePar
         s_count = 0;
         s_thr = 0ull;
     }
+    if (tid < kSlots * 4)  // -inf sentinels behind the data of every slot: neighbours outside the image, idle columns
+        c.ring[(size_t)(tid >> 2) * p.slot_floats + p.slot_floats - 4 + (tid & 3)] = neg_inf();
     __syncthreads();
 
-    auto row_f_lo = [&](int r) -> long long { return (((long long)b * H + r) * W + px_lo) * stride; };
-    auto row_is_bulk = [&](int r) -> bool {
-        if (!p.use_bulk) return false;
-        const long long a_hi = ((((long long)b * H + r) * W + px_hi) * stride + 3) & ~3LL;
-        return a_hi <= p.total_floats;
-    };
-    auto load_row = [&](int r) {
-        float* dst = ring + (size_t)((r - r_first) % kSlots) * p.slot_floats;
-        const long long f_lo = row_f_lo(r);
-        const long long f_hi = f_lo + (long long)(px_hi - px_lo) * stride;
-        const long long a_lo = f_lo & ~3LL;
-        if (row_is_bulk(r)) {
-            if (tid == 0) {
-                const long long a_hi = (f_hi + 3) & ~3LL;
-                const uint32_t bytes = (uint32_t)((a_hi - a_lo) * 4);
-                uint64_t* bar = &full_bar[(r - r_first) % kSlots];
-                mbar_arrive_expect_tx(bar, bytes);
-                bulk_g2s(dst, p.yp + a_lo, bytes, bar);
-            }
-        } else {
-            const int lead = (int)(f_lo - a_lo), n = (int)(f_hi - f_lo);
-            const float* src = p.yp + f_lo;
-            for (int i = tid; i < n; i += kThreads) dst[lead + i] = src[i];
-        }
-    };
+    for (int r = r_first; r <= c.r_last && r < c.ra - 1 + kSlots; ++r) load_row(c, r, tid);
 
-    for (int r = r_first; r <= r_last && r < r_first + kSlots; ++r) load_row(r);
-
-    // fixed element-columns of this thread
-    int lo[kE];
-    unsigned int flags = 0;  // bit k: valid, bit 8+k: has left neighbour, bit 16+k: has right neighbour
+    // fixed element-columns of this thread: addresses (inside slot 0) of the value and of its two x-neighbours
+    const float* pv[kE];
+    const float* pl[kE];
+    const float* pr[kE];
+    const float* const sent = c.ring + p.slot_floats - 4;
 #pragma unroll
     for (int k = 0; k < kE; ++k) {
         const int e = tid + k * kThreads;
-        lo[k] = 0;
+        pv[k] = pl[k] = pr[k] = sent;
         if (e < n_elem) {
-            int xl = hm == 1 ? e : __float2int_rz(((float)e + 0.5f) * p.inv_hm);
-            const int c = e - xl * hm;
+            const int xl = hm == 1 ? e : __float2int_rz(((float)e + 0.5f) * p.inv_hm);
+            const int ch = e - xl * hm;
             const int x = xa + xl;
-            lo[k] = (x - px_lo) * stride + c;
-            flags |= 1u << k;
-            if (x > 0) flags |= 1u << (8 + k);
-            if (x < W - 1) flags |= 1u << (16 + k);
+            pv[k] = c.ring + c.lead + (x - px_lo) * stride + ch;
+            if (x > 0) pl[k] = pv[k] - stride;
+            if (x < W - 1) pr[k] = pv[k] + stride;
         }
     }
-    float vc[kE], hp[kE], hc[kE];
+    float hA[kE], hB[kE], hC[kE], hD[kE], va[kE], vb[kE];
 #pragma unroll
-    for (int k = 0; k < kE; ++k) vc[k] = hp[k] = hc[k] = neg_inf();
+    for (int k = 0; k < kE; ++k) hA[k] = hB[k] = hC[k] = hD[k] = va[k] = vb[k] = neg_inf();
 
     uint32_t phase_bits = 0;
     unsigned long long thr = 0ull;
-    int trigger = 0;  // this thread received a buffer position at/after the compaction mark
-    const unsigned int flat_x0 = (unsigned)(xa * hm + tid);
+    float thr_f = __uint_as_float(1u);  // smallest positive float: "score > 0" and "score >= threshold" in one compare
+    int trigger = 0;                    // this thread received a buffer position at/after the compaction mark
 
-    for (int r = ra - 1; r <= rb; ++r) {
-        const bool in_img = (r >= 0 && r < H);
-        float vn[kE], hn[kE];
-        if (in_img) {
-            const int s = (r - r_first) % kSlots;
-            if (row_is_bulk(r)) {
-                mbar_wait(&full_bar[s], (phase_bits >> s) & 1u);
-                phase_bits ^= 1u << s;
-            } else {
-                __syncthreads();
-            }
-            const float* __restrict__ base = ring + (size_t)s * p.slot_floats + (int)(row_f_lo(r) & 3LL);
-#pragma unroll
-            for (int k = 0; k < kE; ++k) {
-                float v = neg_inf(), l = neg_inf(), rt = neg_inf();
-                if (flags & (1u << k)) {
-                    v = base[lo[k]];
-                    if (flags & (1u << (8 + k))) l = base[lo[k] - stride];
-                    if (flags & (1u << (16 + k))) rt = base[lo[k] + stride];
-                }
-                vn[k] = v;
-                hn[k] = fmaxf(v, fmaxf(l, rt));
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < kE; ++k) vn[k] = hn[k] = neg_inf();
-        }
-        const int yt = r - 1;  // row whose 3x3 neighbourhood is now complete
-        if (yt >= ra && yt < rb) {
-            const unsigned int flat_row = (unsigned)yt * (unsigned)(W * hm) + flat_x0;
-#pragma unroll
-            for (int k = 0; k < kE; ++k) {
-                const float m = fmaxf(hp[k], fmaxf(hc[k], hn[k]));
-                if ((flags & (1u << k)) && vc[k] >= m && vc[k] > 0.f) {
-                    const unsigned int flat = flat_row + (unsigned)(k * kThreads);
-                    const unsigned long long key =
-                        ((unsigned long long)__float_as_uint(vc[k]) << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
-                    if (key > thr) {
-                        const int pos = atomicAdd(&s_count, 1);
-                        cand[pos] = key;
-                        trigger |= (pos >= p.compact_at);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < kE; ++k) {
-            hp[k] = hc[k];
-            hc[k] = hn[k];
-            vc[k] = vn[k];
-        }
-        // slot consumed by everyone; appends of this row are visible.  The OR of the per-thread marks is the only
-        // race-free uniform way to learn "buffer passed the mark" (fast threads may already append for the next row
-        // once they leave a plain barrier, so s_count itself must not be sampled here).
-        const int do_compact = __syncthreads_or(trigger);
-        if (in_img && r + kSlots <= r_last) load_row(r + kSlots);
-        if (do_compact) {  // every thread is in here, so s_count is frozen
-            select_topk(cand, s_count, p.K, hist, keep, s_misc, &s_thr);
-            if (tid == 0) s_count = p.K;
-            trigger = 0;
-            __syncthreads();
-            thr = s_thr;
-        }
+    // rows ra-1 .. rb.  Four h register sets rotate with period 4 (= ring depth, so the slot is a compile-time constant),
+    // the two value sets with period 2: no register moves between rows.
+#define CVM_STEP(J, HP, HC, HN, VC, VN)                                                                       \
+    if (r + J <= c.rb) row_step<J>(c, r + J, tid, pv, pl, pr, HP, HC, HN, VC, VN, phase_bits, thr, thr_f, trigger)
+    for (int r = c.ra - 1; r <= c.rb; r += 4) {
+        CVM_STEP(0, hC, hD, hA, vb, va);
+        CVM_STEP(1, hD, hA, hB, va, vb);
+        CVM_STEP(2, hA, hB, hC, vb, va);
+        CVM_STEP(3, hB, hC, hD, va, vb);
     }
+#undef CVM_STEP
 
     int n = s_count;
     if (n > p.K) {
-        select_topk(cand, n, p.K, hist, keep, s_misc, &s_thr);
+        select_topk(c.cand, n, p.K, hist, c.keep, s_misc, &s_thr);
         n = p.K;
     }
     unsigned long long* out = p.keys + (size_t)blockIdx.x * p.K;
-    for (int i = tid; i < n; i += kThreads) out[i] = cand[i];
+    for (int i = tid; i < n; i += kThreads) out[i] = c.cand[i];
     if (tid == 0) p.counts[blockIdx.x] = n;
 }
 
@@ -429,7 +474,7 @@ int plan_tiling(const cvm_layout* L, int stride, int B, int K, Tiling* t) {
     if ((long long)nsy * t->nbx * K > 16384) return CVM_ERR_ARG;
     t->SR = (H + nsy - 1) / nsy;
     t->nsy = (H + t->SR - 1) / t->SR;
-    t->slot_floats = (((t->TW + 2) * stride + 8) + 3) & ~3;
+    t->slot_floats = ((((t->TW + 2) * stride + 8) + 3) & ~3) + 4;   // + 4 sentinel floats
     t->compact_at = K + kSlack;
     t->cap = t->compact_at + t->TW * hm;
     t->smem_stream = (size_t)kSlots * t->slot_floats * 4 + (size_t)t->cap * 8 + (size_t)K * 8;

@@ -44,6 +44,23 @@ __device__ __forceinline__ float pow_b(float x, const LossParams& p) {
     return powf(x, p.fb);
 }
 
+// log(clip(1 - q, .01, .99)) of the negative term (loss.py:47).  z = clip(q) is exact, so for small z the series
+// log1p(-z) = -z - z^2/2 - ... (6 terms, truncation < 1e-8 relative for z < 1/16) avoids both the rounding of 1 - q and
+// the absolute-error floor of MUFU.LG2 near 1; elsewhere |log| >= 0.0645 and lg2.approx (abs err 2^-22) is < 3e-6 relative.
+__device__ __forceinline__ float log_one_minus(float q) {
+    const float z = fminf(fmaxf(q, 0.01f), 0.99f);
+    float s = fmaf(z, 1.0f / 6.0f, 0.2f);
+    s = fmaf(z, s, 0.25f);
+    s = fmaf(z, s, 1.0f / 3.0f);
+    s = fmaf(z, s, 0.5f);
+    s = fmaf(z, s, 1.0f);
+    const float small = -z * s;
+    float lg;  // 1 - z is in [0.01, 0.99]: no denormal handling needed around MUFU.LG2
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(1.0f - z));
+    const float big = lg * 0.69314718055994530942f;
+    return z < 0.0625f ? small : big;
+}
+
 // one regression field at a peak pixel: sum_k |term| (loss.py:115-128), fp64 from fp32 inputs
 __device__ double field_term(int kind, const float* t, const float* q, int size) {
     double s = 0.0;
@@ -154,8 +171,7 @@ __global__ void __launch_bounds__(kThreads) loss_fwd_kernel(const LossParams p) 
             const float q = Q[px * st_p + c];
             const float w = wch >= 0 ? T[px * st_t + wch] : 1.0f;
             if (y < 1.0f) {  // neg_mask (loss.py:36,43-48)
-                const float l = logf(fminf(fmaxf(1.0f - q, 0.01f), 0.99f));
-                sN += (-(pow_b(1.0f - y, p) * pow_a(q, p)) * l) * w;
+                sN += (-(pow_b(1.0f - y, p) * pow_a(q, p)) * log_one_minus(q)) * w;
             } else if (y == 1.0f) {  // pos_mask (loss.py:35,38-42)
                 const float l = logf(fminf(fmaxf(q, 0.01f), 0.99f));
                 sP += (-pow_a(1.0f - q, p) * l) * w;
@@ -261,6 +277,162 @@ int loss_grid(long long n_spans, size_t smem_bytes) {
     return (int)g;
 }
 
+// Rare work for a pixel that holds at least one heatmap value == 1.0: positive focal terms, counts and the regression
+// fields.  Kept out of line, accumulating into a local-memory array, so that it costs the hot loop no registers.
+// cold[0] = P, cold[1] = n_pos, cold[2] = n_obj, cold[3 + f] = field sums.
+__device__ __noinline__ void peak_pixel(const float* T, const float* Q, int hm, float w, const LossParams& p, double* cold) {
+    bool first = true;
+    float sP = 0.f;
+    for (int c = 0; c < hm; ++c) {
+        if (T[c] == 1.0f) {                                                     // pos_mask, loss.py:35,38-42
+            const float q = Q[c];
+            sP += (-pow_a(1.0f - q, p) * logf(fminf(fmaxf(q, 0.01f), 0.99f))) * w;
+            cold[1] += 1.0;
+            if (first) {                                                        // pos_mask reduce_max, loss.py:110-113
+                first = false;
+                cold[2] += 1.0;
+                for (int f = 0; f < p.n_fields; ++f)
+                    cold[3 + f] += field_term(p.f_kind[f], T + p.f_off[f], Q + p.f_off[f], p.f_size[f]);
+            }
+        }
+    }
+    cold[0] += (double)sP;
+}
+
+// ---- fast path: channel counts known at compile time, one pixel per thread ------------------------------------------
+// All shared-memory offsets become immediates, the heatmap loop is fully unrolled (HM independent element chains per
+// thread) and the rare "this pixel holds a peak" work is taken out of the hot loop.
+template <int HM, int ST_T, int ST_P>
+__global__ void __launch_bounds__(kThreads) loss_fwd_fast_kernel(const LossParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full_bar[kStages];
+    __shared__ double red[kThreads / 32][CVM_NPART];
+
+    float* const ring = reinterpret_cast<float*>(smem_raw);
+    const int tid = threadIdx.x;
+    constexpr int TP = kThreads;  // one pixel per thread per span
+    constexpr size_t t_floats = (size_t)TP * ST_T;
+    constexpr size_t stage_floats = (size_t)TP * (ST_T + ST_P);
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const long long n_full = p.use_bulk ? p.n_pixels / TP : 0;  // spans below this index are full and bulk-loadable
+    auto load_span = [&](long long span, int s) {
+        float* dst_t = ring + (size_t)s * stage_floats;
+        float* dst_p = dst_t + t_floats;
+        const float* src_t = p.yt + span * (long long)(TP * ST_T);
+        const float* src_p = p.yp + span * (long long)(TP * ST_P);
+        if (span < n_full) {
+            if (tid == 0) {
+                constexpr uint32_t bt = (uint32_t)(t_floats * 4), bq = (uint32_t)((size_t)TP * ST_P * 4);
+                mbar_arrive_expect_tx(&full_bar[s], bt + bq);
+                bulk_g2s(dst_t, src_t, bt, &full_bar[s]);
+                bulk_g2s(dst_p, src_p, bq, &full_bar[s]);
+            }
+        } else {
+            const long long left = p.n_pixels - span * TP;
+            const int np = left < TP ? (int)left : TP;
+            for (int i = tid; i < np * ST_T; i += kThreads) dst_t[i] = src_t[i];
+            for (int i = tid; i < np * ST_P; i += kThreads) dst_p[i] = src_p[i];
+        }
+    };
+
+    const long long gstride = gridDim.x;
+    for (int s = 0; s < kStages; ++s) {
+        const long long span = blockIdx.x + (long long)s * gstride;
+        if (span < p.n_spans) load_span(span, s);
+    }
+
+    double accN = 0.0;
+    double cold[3 + CVM_MAX_FIELDS];
+#pragma unroll
+    for (int f = 0; f < 3 + CVM_MAX_FIELDS; ++f) cold[f] = 0.0;
+    uint32_t phase_bits = 0;
+    const int wch = p.wch;
+    float sN = 0.f;
+    int folded = 0;
+
+    for (int it = 0;; ++it) {
+        const long long span = blockIdx.x + (long long)it * gstride;
+        if (span >= p.n_spans) break;
+        const int s = it % kStages;
+        int np = TP;
+        if (span < n_full) {
+            mbar_wait(&full_bar[s], (phase_bits >> s) & 1u);
+            phase_bits ^= (1u << s);
+        } else {
+            __syncthreads();
+            const long long left = p.n_pixels - span * TP;
+            np = left < TP ? (int)left : TP;
+        }
+        const float* __restrict__ T = ring + (size_t)s * stage_floats + tid * ST_T;
+        const float* __restrict__ Q = ring + (size_t)s * stage_floats + t_floats + tid * ST_P;
+        if (tid < np) {
+            const float w = wch >= 0 ? T[wch] : 1.0f;
+            float acc = 0.f, ymax = 0.f;
+#pragma unroll
+            for (int c = 0; c < HM; ++c) {
+                const float y = T[c];
+                const float q = Q[c];
+                const float t = 1.0f - y, t2 = t * t;                                        // alpha = 2, beta = 4 only
+                const float nl = ((t2 * t2) * (q * q)) * log_one_minus(q);                  // -neg_loss, loss.py:43-48
+                acc += (y < 1.0f) ? nl : 0.0f;                                              // neg_mask, loss.py:36
+                ymax = fmaxf(ymax, y);
+            }
+            sN = fmaf(-acc, w, sN);
+            if (ymax >= 1.0f) peak_pixel(T, Q, HM, w, p, cold);  // rare: a few dozen pixels per image (re-tests == 1.0)
+        }
+        if (++folded == 8) {  // short fp32 chains (<= 8*HM addends), everything above in fp64
+            accN += (double)sN;
+            sN = 0.f;
+            folded = 0;
+        }
+        __syncthreads();  // everyone is done with stage s
+        const long long next = span + (long long)kStages * gstride;
+        if (next < p.n_spans) load_span(next, s);
+    }
+    accN += (double)sN;
+
+    double v[CVM_NPART];
+    v[0] = cold[0];
+    v[1] = accN;
+    v[2] = cold[1];
+    v[3] = cold[2];
+#pragma unroll
+    for (int f = 0; f < CVM_MAX_FIELDS; ++f) v[4 + f] = cold[3 + f];
+#pragma unroll
+    for (int k = 4 + CVM_MAX_FIELDS; k < CVM_NPART; ++k) v[k] = 0.0;
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int k = 0; k < CVM_NPART; ++k) {
+        const double r = warp_sum(v[k]);
+        if (lane == 0) red[warp][k] = r;
+    }
+    __syncthreads();
+    if (tid < CVM_NPART) {
+        double r = 0.0;
+        for (int wi = 0; wi < kThreads / 32; ++wi) r += red[wi][tid];
+        p.block_partials[(size_t)blockIdx.x * CVM_NPART + tid] = r;
+    }
+}
+
+template <int HM, int ST_T, int ST_P>
+int launch_loss_fast(LossParams& p, cudaStream_t st, int* grid_out) {
+    p.TP = kThreads;
+    p.n_spans = (p.n_pixels + p.TP - 1) / p.TP;
+    const size_t smem = (size_t)kStages * kThreads * (ST_T + ST_P) * 4;
+    const int grid = loss_grid(p.n_spans, smem);
+    CVM_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_fast_kernel<HM, ST_T, ST_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    loss_fwd_fast_kernel<HM, ST_T, ST_P><<<grid, kThreads, smem, st>>>(p);
+    CVM_CHECK_LAUNCH("loss_fwd_fast_kernel");
+    *grid_out = grid;
+    return CVM_OK;
+}
+
 int check_layout_for_loss(const cvm_layout* L, int st_t, int st_p) {
     CVM_CHECK_ARG(L != nullptr, "layout is NULL");
     CVM_CHECK_ARG(L->hm >= 1 && L->hm <= 64, "hm=%d out of range [1,64]", L->hm);
@@ -324,10 +496,26 @@ extern "C" int cvm_loss_fwd(const cvm_layout* L, const float* y_true, int y_true
     p.use_bulk = cvm_aligned16(y_true) && cvm_aligned16(y_pred);
     p.block_partials = static_cast<double*>(ws);
 
-    const int grid = loss_grid(p.n_spans, smem);
-    CVM_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    loss_fwd_kernel<<<grid, kThreads, smem, st>>>(p);
-    CVM_CHECK_LAUNCH("loss_fwd_kernel");
+    int grid = 0;
+    // compile-time layouts: (hm, y_true stride, y_pred stride) of BASELINE.json's configs and the reference defaults
+#define CVM_LOSS_FAST(HM_, ST_T_, ST_P_)                                              \
+    if (grid == 0 && p.a_is2 && p.b_is4 && L->hm == HM_ && y_true_stride == ST_T_ && y_pred_stride == ST_P_) { \
+        rc = launch_loss_fast<HM_, ST_T_, ST_P_>(p, st, &grid);                        \
+        if (rc != CVM_OK) return rc;                                                  \
+    }
+    CVM_LOSS_FAST(10, 15, 14)   // configs 1-3: 10-class heatmaps
+    CVM_LOSS_FAST(10, 17, 16)   // config 4: + track_offset
+    CVM_LOSS_FAST(10, 22, 20)   // config 5: CenterNet slice inside the multitask tensors
+    CVM_LOSS_FAST(1, 16, 15)    // reference-exact layout, 10 classes
+    CVM_LOSS_FAST(1, 12, 11)    // reference defaults (6 classes)
+    CVM_LOSS_FAST(1, 14, 13)    // reference CenterTracker defaults
+#undef CVM_LOSS_FAST
+    if (grid == 0) {            // any other layout: runtime-parameterised kernel
+        grid = loss_grid(p.n_spans, smem);
+        CVM_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        loss_fwd_kernel<<<grid, kThreads, smem, st>>>(p);
+        CVM_CHECK_LAUNCH("loss_fwd_kernel");
+    }
     loss_reduce_kernel<<<1, 256, 0, st>>>(p.block_partials, grid, partials);
     CVM_CHECK_LAUNCH("loss_reduce_kernel");
     return CVM_OK;

@@ -17,7 +17,7 @@
 namespace {
 
 constexpr int kThreads = 256;   // power of two: column ownership is x & (kThreads - 1)
-constexpr int kMaxObjSmem = 64;  // objects are processed in chunks of this many
+constexpr int kMaxObjSmem = 96;  // objects are processed in chunks of this many
 
 struct RenderParams {
     const cvm_obj* objs;
@@ -29,7 +29,8 @@ struct RenderParams {
     int n_planes;      // heatmap planes kept in smem (hm)
     int wch;           // weights channel in the output pixel, -1 = none (prev-frame heatmap)
     int rows;          // rows per tile
-    int tiles_per_img;
+    int tiles_per_band;  // tiles (of `rows` rows) handled by one CTA
+    int bands_per_img;
     int plane_stride;  // rows*W + pad
     int per_class;     // 1: heat plane = obj.cls (Profile N); 0: plane 0 (reference as shipped)
     int force_explicit;
@@ -103,129 +104,156 @@ __device__ __forceinline__ void derive(const cvm_obj& o, const RenderParams& p, 
 __global__ void __launch_bounds__(kThreads) render_kernel(const RenderParams p) {
     extern __shared__ __align__(16) float planes[];  // [n_planes + 1][plane_stride]; last = weights
     __shared__ ObjDerived sobj[kMaxObjSmem];
+    __shared__ int s_list[kMaxObjSmem];
+    __shared__ int s_nlist;
 
     const int tid = threadIdx.x;
-    const int b = blockIdx.x / p.tiles_per_img;
-    const int tile = blockIdx.x - b * p.tiles_per_img;
-    const int ya = tile * p.rows;
-    const int yb = min(p.H, ya + p.rows);
-    const int nrows = yb - ya;
-    const int W = p.W;
-    const int PS = p.plane_stride;
-    float* const wplane = planes + (size_t)p.n_planes * PS;
-
-    // init: heat = 0, weights = 1 (processor.py:267-268)
-    for (int i = tid; i < p.n_planes * PS; i += kThreads) planes[i] = 0.f;
-    for (int i = tid; i < PS; i += kThreads) wplane[i] = 1.f;
-    __syncthreads();  // planes are handed over from linear-index owners to column owners
+    const int b = blockIdx.x / p.bands_per_img;
+    const int band = blockIdx.x - b * p.bands_per_img;
+    const int W = p.W, PS = p.plane_stride;
+    const int Cout = p.Cout, hm = p.n_planes, wch = p.wch;
+    float* const wplane = planes + (size_t)hm * PS;
+    const int band_ya = band * p.tiles_per_band * p.rows;
+    const int band_yb = min(p.H, band_ya + p.tiles_per_band * p.rows);
 
     const int o_begin = p.obj_offsets[b], o_end = p.obj_offsets[b + 1];
-    float* const out_img = p.out + (size_t)b * p.H * W * p.Cout;
-
-    // ---- splat: objects in chunks; each thread owns columns tid, tid+256, ... for all rows of the tile ----
+    float* const out_img = p.out + (size_t)b * p.H * W * Cout;
+    const bool single_chunk = (o_end - o_begin) <= kMaxObjSmem;
     int loaded_base = -1;  // which chunk of objects currently sits in sobj
-    for (int base = o_begin; base < o_end; base += kMaxObjSmem) {
-        const int n = min(kMaxObjSmem, o_end - base);
-        __syncthreads();  // previous chunk consumed
-        if (tid < n) derive(p.objs[base + tid], p, sobj[tid]);
-        loaded_base = base;
-        __syncthreads();
-        for (int oi = 0; oi < n; ++oi) {
-            const ObjDerived& d = sobj[oi];
-            const int r0 = max(d.y0, ya), r1 = min(d.y1, yb);
-            if (r0 >= r1 || d.x0 >= d.x1) continue;  // uniform across the CTA
-            float* const hp = planes + (size_t)d.plane * PS;
-            for (int x = d.x0 + ((tid - d.x0) & (kThreads - 1)); x < d.x1; x += kThreads) {  // column x belongs to thread x % 256
-                const double dx = (double)(x - d.cx);
-                const double ax = dx * dx * d.inv2vx;
-                for (int y = r0; y < r1; ++y) {
-                    const double dy = (double)(y - d.cy);
-                    const double g = exp(-(ax + dy * dy * d.inv2vy));                 // processor.py:34-36
-                    const int idx = (y - ya) * W + x;
-                    hp[idx] = fmaxf(hp[idx], (float)(g * d.peak));                    // :37
-                    if (p.wch >= 0) wplane[idx] = fminf(wplane[idx], (float)(1.0 - d.rw * g));   // :38
-                }
-            }
-        }
+    if (single_chunk && o_end > o_begin) {  // the common case: derive once per band, reuse for every tile
+        if (tid < o_end - o_begin) derive(p.objs[o_begin + tid], p, sobj[tid]);
+        loaded_base = o_begin;
     }
 
-    // ---- ignore areas: weights = 0, input-px numbers used as mask indices (processor.py:318-323) ----
-    if (p.ignore != nullptr && p.wch >= 0) {
-        const int i_begin = p.ign_offsets[b], i_end = p.ign_offsets[b + 1];
-        for (int i = i_begin; i < i_end; ++i) {
-            const cvm_box bx = p.ignore[i];
-            const int sy = max((int)bx.y, 0), ey = min(max((int)(bx.y + bx.h), 0), p.H);
-            const int sx = max((int)bx.x, 0), ex = min(max((int)(bx.x + bx.w), 0), W);
-            const int r0 = max(sy, ya), r1 = min(ey, yb);
-            for (int x = sx + ((tid - sx) & (kThreads - 1)); x < ex; x += kThreads)   // same column ownership as the splat
-                for (int y = r0; y < r1; ++y) wplane[(y - ya) * W + x] = 0.f;
-        }
-    }
-    __syncthreads();
-
-    // ---- compose NHWC and stream out ----
-    const int Cout = p.Cout, hm = p.n_planes, wch = p.wch;
-    const int tile_floats = nrows * W * Cout;
-    float* const out_tile = out_img + (size_t)ya * W * Cout;
-    auto value_at = [&](int px, int ch) -> float {
-        if (ch < hm) return planes[(size_t)ch * PS + px];
-        if (ch == wch) return wplane[px];
-        return 0.f;
-    };
-    if (p.vec_ok) {
-        const float inv_c = 1.0f / (float)Cout;
-        const int nvec = tile_floats >> 2;
-        for (int q = tid; q < nvec; q += kThreads) {
-            const int f = q << 2;
-            int px = __float2int_rz(((float)f + 0.5f) * inv_c);
-            int ch = f - px * Cout;
-            if (ch < 0) {  // guard the float reciprocal for very large tiles
-                --px;
-                ch += Cout;
-            } else if (ch >= Cout) {
-                ++px;
-                ch -= Cout;
-            }
-            float v[4];
+    // compose mapping (vector path): the NHWC pattern repeats every 4 pixels = Cout float4s.  Thread t < NA handles float4
+    // slot r = t % Cout of pixel groups g = t / Cout, + GS, ...; which plane/pixel feeds its 4 floats never changes.
+    const int GS = kThreads / Cout, NA = GS * Cout;
+    int coff[4] = {-1, -1, -1, -1};
+    const int cr = tid % Cout, cg0 = tid / Cout;
+    if (p.vec_ok && tid < NA) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                v[k] = value_at(px, ch);
-                if (++ch == Cout) {
-                    ch = 0;
-                    ++px;
-                }
-            }
-            st_cs_f4(reinterpret_cast<float4*>(out_tile) + q, make_float4(v[0], v[1], v[2], v[3]));
-        }
-    } else {
-        for (int f = tid; f < tile_floats; f += kThreads) {
-            const int px = f / Cout;
-            out_tile[f] = value_at(px, f - px * Cout);
+        for (int k = 0; k < 4; ++k) {
+            const int f = 4 * cr + k, pig = f / Cout, ch = f - pig * Cout;
+            if (ch < hm)
+                coff[k] = ch * PS + pig;
+            else if (ch == wch)
+                coff[k] = hm * PS + pig;
         }
     }
 
-    // ---- centre scatter (processor.py:288-299): patched after the tile is out; last object wins per pixel ----
+    for (int ya = band_ya; ya < band_yb; ya += p.rows) {
+        const int yb = min(band_yb, ya + p.rows);
+        const int nrows = yb - ya;
+
+        // ---- init: heat = 0, weights = 1 (processor.py:267-268) ----
+        {
+            float4* p4 = reinterpret_cast<float4*>(planes);
+            const int n4 = (hm * PS) >> 2;
+            for (int i = tid; i < n4; i += kThreads) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = (n4 << 2) + tid; i < hm * PS; i += kThreads) planes[i] = 0.f;
+            for (int i = tid; i < PS; i += kThreads) wplane[i] = 1.f;
+            if (tid == 0) s_nlist = 0;
+        }
+        __syncthreads();  // planes are handed over from linear-index owners to column owners
+
+        // ---- splat: each thread owns columns x with x % 256 == tid for all rows of the tile ----
+        for (int base = o_begin; base < o_end; base += kMaxObjSmem) {
+            const int n = min(kMaxObjSmem, o_end - base);
+            if (loaded_base != base) {  // only with more than one chunk of objects
+                __syncthreads();
+                if (tid < n) derive(p.objs[base + tid], p, sobj[tid]);
+                loaded_base = base;
+                if (tid == 0) s_nlist = 0;
+                __syncthreads();
+            }
+            if (tid < n) {  // objects whose window touches this tile (order is irrelevant for max/min)
+                const ObjDerived& d = sobj[tid];
+                if (max(d.y0, ya) < min(d.y1, yb) && d.x0 < d.x1) s_list[atomicAdd(&s_nlist, 1)] = tid;
+            }
+            __syncthreads();
+            const int nl = s_nlist;
+            for (int li = 0; li < nl; ++li) {
+                const ObjDerived& d = sobj[s_list[li]];
+                const int r0 = max(d.y0, ya), r1 = min(d.y1, yb);
+                float* const hp = planes + (size_t)d.plane * PS;
+                for (int x = d.x0 + ((tid - d.x0) & (kThreads - 1)); x < d.x1; x += kThreads) {
+                    const double dx = (double)(x - d.cx);
+                    const double ax = dx * dx * d.inv2vx;
+                    for (int y = r0; y < r1; ++y) {
+                        const double dy = (double)(y - d.cy);
+                        const double g = exp(-(ax + dy * dy * d.inv2vy));                 // processor.py:34-36
+                        const int idx = (y - ya) * W + x;
+                        hp[idx] = fmaxf(hp[idx], (float)(g * d.peak));                    // :37
+                        if (wch >= 0) wplane[idx] = fminf(wplane[idx], (float)(1.0 - d.rw * g));   // :38
+                    }
+                }
+            }
+        }
+
+        // ---- ignore areas: weights = 0, input-px numbers used as mask indices (processor.py:318-323) ----
+        if (p.ignore != nullptr && wch >= 0) {
+            const int i_begin = p.ign_offsets[b], i_end = p.ign_offsets[b + 1];
+            for (int i = i_begin; i < i_end; ++i) {
+                const cvm_box bx = p.ignore[i];
+                const int sy = max((int)bx.y, 0), ey = min(max((int)(bx.y + bx.h), 0), p.H);
+                const int sx = max((int)bx.x, 0), ex = min(max((int)(bx.x + bx.w), 0), W);
+                const int r0 = max(sy, ya), r1 = min(ey, yb);
+                for (int x = sx + ((tid - sx) & (kThreads - 1)); x < ex; x += kThreads)   // same column ownership as the splat
+                    for (int y = r0; y < r1; ++y) wplane[(y - ya) * W + x] = 0.f;
+            }
+        }
+        __syncthreads();
+
+        // ---- compose NHWC and stream out ----
+        const int tile_floats = nrows * W * Cout;
+        float* const out_tile = out_img + (size_t)ya * W * Cout;
+        if (p.vec_ok && ((nrows * W) & 3) == 0) {  // a ragged last tile may not be whole groups of 4 pixels
+            if (tid < NA) {
+                const int n_groups = (nrows * W) >> 2;
+                float4* dst = reinterpret_cast<float4*>(out_tile) + tid;
+                for (int g = cg0; g < n_groups; g += GS, dst += NA) {
+                    const int g4 = g << 2;
+                    float4 v;
+                    v.x = coff[0] >= 0 ? planes[coff[0] + g4] : 0.f;
+                    v.y = coff[1] >= 0 ? planes[coff[1] + g4] : 0.f;
+                    v.z = coff[2] >= 0 ? planes[coff[2] + g4] : 0.f;
+                    v.w = coff[3] >= 0 ? planes[coff[3] + g4] : 0.f;
+                    st_cs_f4(dst, v);
+                }
+            }
+        } else {
+            for (int f = tid; f < tile_floats; f += kThreads) {
+                const int px = f / Cout, ch = f - px * Cout;
+                out_tile[f] = ch < hm ? planes[(size_t)ch * PS + px] : (ch == wch ? wplane[px] : 0.f);
+            }
+        }
+        __syncthreads();  // the planes are re-initialised for the next tile
+    }
+
+    // ---- centre scatter (processor.py:288-299): patched after the band is out; last object wins per pixel ----
     if (p.off_class < 0 && p.off_roff < 0 && p.off_box < 0 && p.off_track < 0) return;
     for (int base = o_begin; base < o_end; base += kMaxObjSmem) {
         const int n = min(kMaxObjSmem, o_end - base);
-        __syncthreads();  // orders the tile stores above (and the previous chunk) before the patches
-        if (loaded_base != base) {  // only when the image has more than one chunk of objects
+        if (loaded_base != base) {
+            __syncthreads();
             if (tid < n) derive(p.objs[base + tid], p, sobj[tid]);
             loaded_base = base;
             __syncthreads();
         }
         if (tid < n) {
             const ObjDerived& d = sobj[tid];
-            if (d.scy >= ya && d.scy < yb && d.scx >= 0) {
+            if (d.scy >= band_ya && d.scy < band_yb && d.scx >= 0) {
                 // a later object (list order) at the same pixel overwrites r_offset/fullbox/track
                 bool last = true;
                 for (int j = base + tid + 1; j < o_end && last; ++j) {
-                    ObjDerived e;
-                    if (j - base < n)
-                        e = sobj[j - base];
-                    else
+                    if (j - base < n) {
+                        const ObjDerived& e = sobj[j - base];
+                        if (e.scx == d.scx && e.scy == d.scy) last = false;
+                    } else {
+                        ObjDerived e;
                         derive(p.objs[j], p, e);
-                    if (e.scx == d.scx && e.scy == d.scy) last = false;
+                        if (e.scx == d.scx && e.scy == d.scy) last = false;
+                    }
                 }
                 float* px = out_img + ((size_t)d.scy * W + d.scx) * Cout;
                 if (p.off_class >= 0 && d.cls >= 0 && p.off_class + d.cls < Cout) px[p.off_class + d.cls] = 1.0f;   // :290
@@ -248,31 +276,37 @@ __global__ void __launch_bounds__(kThreads) render_kernel(const RenderParams p) 
     }
 }
 
-int pick_rows(int H, int W, int n_planes_total, int B, size_t* smem_bytes, int* plane_stride) {
-    // as many rows as keep the planes <= ~64 KB (3 CTAs/SM) while leaving enough tiles to fill the machine twice
+int pick_rows(int H, int W, int n_planes_total, size_t* smem_bytes, int* plane_stride) {
+    // as many rows as keep the planes <= ~36 KB (>= 4 CTAs/SM by shared memory), at least one
     int rows = 1;
-    const size_t budget = 64 * 1024;
+    const size_t budget = 36 * 1024;
     while (rows < H && (size_t)(rows * 2) * W * n_planes_total * 4 <= budget) rows *= 2;
-    const long long want_tiles = 2LL * cvm_num_sms();
-    while (rows > 1 && (long long)B * ((H + rows - 1) / rows) < want_tiles) rows >>= 1;
-    *plane_stride = rows * W + 1;
-    *smem_bytes = (size_t)(*plane_stride) * n_planes_total * 4;
+    *plane_stride = ((rows * W + 3) & ~3) + 1;   // odd stride: plane-to-plane bank offset of 1
+    *smem_bytes = (size_t)(*plane_stride) * n_planes_total * 4 + 16;
     return rows;
 }
 
 int launch_render(const RenderParams& p0, int B, cudaStream_t st) {
     RenderParams p = p0;
     size_t smem = 0;
-    p.rows = pick_rows(p.H, p.W, p.n_planes + 1, B, &smem, &p.plane_stride);
+    p.rows = pick_rows(p.H, p.W, p.n_planes + 1, &smem, &p.plane_stride);
     if (smem > 200 * 1024) {
         cvm_set_error("render: one row of %d planes x %d px does not fit in shared memory", p.n_planes + 1, p.W);
         return CVM_ERR_ARG;
     }
-    p.tiles_per_img = (p.H + p.rows - 1) / p.rows;
-    // 128-bit stores need every tile start (and the image start) to be 16-byte aligned
-    p.vec_ok = cvm_aligned16(p.out) && (((long long)p.rows * p.W * p.Cout) % 4 == 0) && (((long long)p.H * p.W * p.Cout) % 4 == 0);
+    // a CTA renders a band of consecutive tiles of one image (object records are derived once per band); bands are sized so
+    // that the grid still fills the machine ~4x over
+    const int tiles_per_img = (p.H + p.rows - 1) / p.rows;
+    int tpb = 8;
+    const long long want = 4LL * cvm_num_sms() * 4;
+    while (tpb > 1 && (long long)B * ((tiles_per_img + tpb - 1) / tpb) < want) tpb >>= 1;
+    p.tiles_per_band = tpb;
+    p.bands_per_img = (tiles_per_img + tpb - 1) / tpb;
+    // 128-bit stores need every tile start (and the image start) 16-byte aligned and whole groups of 4 pixels per tile
+    p.vec_ok = cvm_aligned16(p.out) && (((long long)p.rows * p.W) % 4 == 0) && (((long long)p.H * p.W * p.Cout) % 4 == 0) &&
+               p.Cout <= kThreads;
     CVM_CHECK_CUDA(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long grid = (long long)B * p.tiles_per_img;
+    const long long grid = (long long)B * p.bands_per_img;
     if (grid == 0) return CVM_OK;
     CVM_CHECK_ARG(grid < 2147483647LL, "render grid too large");
     render_kernel<<<(unsigned)grid, kThreads, smem, st>>>(p);
