@@ -20,9 +20,10 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kSlots = 4;         // row-segment ring depth
-constexpr int kSlack = 1024;      // extra buffer entries so that compaction is rare
+constexpr int kSlack = 256;       // buffer entries beyond K before a compaction (small: thresholds rise early)
 constexpr int kMaxK = 1024;
 constexpr int kE = 8;             // element-columns per thread
+constexpr int kSlotFloats = 3328;  // ring slot size (13 KB), compile-time so that slot offsets are immediates
 
 struct DecodeParams {
     const float* yp;
@@ -125,14 +126,14 @@ struct StreamCtx {
     long long row_floats_g;   // W * stride
     int row_floats;           // (px_hi - px_lo) * stride
     int lead;                 // data of a row starts `lead` floats into its slot (16-byte granularity of the bulk copy)
-    int slot_floats, r_last, ra, rb, H, K, compact_at, bulk;
+    int r_last, ra, rb, H, K, compact_at, bulk;
     unsigned flat_x0, flat_row_step;
 };
 
 // global -> ring slot (row r lives in slot (r - (ra-1)) & 3): thread 0 with the bulk engine, or everybody with plain loads
 __device__ __forceinline__ void load_row(const StreamCtx& c, int r, int tid) {
     const int i = r - (c.ra - 1), s = i & (kSlots - 1);
-    float* dst = c.ring + (size_t)s * c.slot_floats;
+    float* dst = c.ring + (size_t)s * kSlotFloats;
     const float* src = c.gsrc + (long long)i * c.row_floats_g;       // first needed float
     if (c.bulk) {
         if (tid == 0) {
@@ -145,23 +146,22 @@ __device__ __forceinline__ void load_row(const StreamCtx& c, int r, int tid) {
     }
 }
 
-// One row step: bring row r's values/3-tap maxima into (vn, hn), test row r-1 with (hp, hc, hn, vc), release the slot.
-// SLOT (= step index mod 4) is a compile-time constant, so every shared load is [per-thread offset + uniform slot base].
+// One row: bring row r's values / 3-tap maxima into (vn, hn), then test row r-1 with (hp, hc, hn, vc).
+// SLOT (= step index mod 4) and the slot size are compile-time constants: every shared load is [register + immediate].
 template <int SLOT>
-__device__ __forceinline__ void row_step(const StreamCtx& c, int r, int tid, const float* const (&pv)[kE],
-                                         const float* const (&pl)[kE], const float* const (&pr)[kE],
-                                         const float (&hp)[kE], const float (&hc)[kE], float (&hn)[kE],
-                                         const float (&vc)[kE], float (&vn)[kE], uint32_t& phase_bits,
-                                         unsigned long long& thr, float& thr_f, int& trigger) {
-    const bool in_img = (r >= 0 && r < c.H);
-    if (in_img) {
+__device__ __forceinline__ void row_compute(const StreamCtx& c, int r, const float* const (&pv)[kE],
+                                            const float* const (&pl)[kE], const float* const (&pr)[kE],
+                                            const float (&hp)[kE], const float (&hc)[kE], float (&hn)[kE],
+                                            const float (&vc)[kE], float (&vn)[kE], uint32_t& phase_bits, float thr_f,
+                                            int& trigger) {
+    if (r >= 0 && r < c.H) {
         if (c.bulk) {
             mbar_wait(&c.full_bar[SLOT], (phase_bits >> SLOT) & 1u);
             phase_bits ^= 1u << SLOT;
         } else {
             __syncthreads();
         }
-        const int so = SLOT * c.slot_floats;
+        constexpr int so = SLOT * kSlotFloats;
 #pragma unroll
         for (int k = 0; k < kE; ++k) {
             const float v = pv[k][so];
@@ -174,35 +174,48 @@ __device__ __forceinline__ void row_step(const StreamCtx& c, int r, int tid, con
     }
     const int yt = r - 1;  // row whose 3x3 neighbourhood is now complete
     if (yt >= c.ra && yt < c.rb) {
-        const unsigned flat_row = (unsigned)yt * c.flat_row_step + c.flat_x0;
+        // hot path: ONE compare per thread and row against the running threshold score (positive by construction); only
+        // threads holding a value that could still make the top K pay for the 3x3 tests.
+        float vmax = vc[0];
 #pragma unroll
-        for (int k = 0; k < kE; ++k) {
-            // peak (value equals its 3x3 max), positive, and not below the running threshold: one compare
-            if (vc[k] >= fmaxf(fmaxf(hp[k], hc[k]), fmaxf(hn[k], thr_f))) {
-                const unsigned flat = flat_row + (unsigned)(k * kThreads);
-                const unsigned long long key =
-                    ((unsigned long long)__float_as_uint(vc[k]) << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
-                if (key > thr) {
-                    const int pos = atomicAdd(c.s_count, 1);
-                    c.cand[pos] = key;
-                    trigger |= (pos >= c.compact_at);
+        for (int k = 1; k < kE; ++k) vmax = fmaxf(vmax, vc[k]);
+        if (vmax >= thr_f) {
+            const unsigned flat_row = (unsigned)yt * c.flat_row_step + c.flat_x0;
+            const unsigned cnt_addr = smem_u32(c.s_count), cand_addr = smem_u32(c.cand);
+#pragma unroll
+            for (int k = 0; k < kE; ++k) {
+                // peak (value equals its 3x3 max) and not below the threshold score.  Scores equal to the threshold score
+                // are appended without looking at the index half of the key: the next select drops them.
+                if (vc[k] >= fmaxf(fmaxf(hp[k], hc[k]), fmaxf(hn[k], thr_f))) {
+                    // a plain (not warp-aggregated) shared atomic: candidates are sparse, a short divergent path matters more
+                    unsigned pos;
+                    asm volatile("atom.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(pos) : "r"(cnt_addr) : "memory");
+                    const unsigned flat = flat_row + (unsigned)(k * kThreads);
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(cand_addr + pos * 8u), "r"(0xFFFFFFFFu - flat),
+                                 "r"(__float_as_uint(vc[k]))
+                                 : "memory");
+                    trigger |= (pos >= (unsigned)c.compact_at);
                 }
             }
         }
     }
-    // slot consumed by everyone; appends of this row are visible.  The OR of the per-thread marks is the only race-free
-    // uniform way to learn "buffer passed the mark" (fast threads may already append for the next row once they leave
+}
+
+// End of a step of two rows: release the two slots, refill them, compact the candidate buffer when it passed the mark.
+__device__ __forceinline__ void step_end(const StreamCtx& c, int r, int tid, float& thr_f, int& trigger) {
+    // slots consumed by everyone; appends of these rows are visible.  The OR of the per-thread marks is the only race-free
+    // uniform way to learn "buffer passed the mark" (fast threads may already append for the next rows once they leave
     // a plain barrier, so *s_count itself must not be sampled here).
     const int do_compact = __syncthreads_or(trigger);
-    // refill this step's slot with the row 4 steps ahead (also after the virtual row -1 of a top stripe, whose slot is idle)
+    // refill with the rows 4 ahead (also after the virtual row -1 of a top stripe, whose slot is idle)
     if (r + kSlots >= 0 && r + kSlots <= c.r_last) load_row(c, r + kSlots, tid);
+    if (r + 1 + kSlots <= c.r_last) load_row(c, r + 1 + kSlots, tid);
     if (do_compact) {  // every thread is in here, so *s_count is frozen
         select_topk(c.cand, *c.s_count, c.K, c.hist, c.keep, c.s_misc, c.s_thr);
         if (tid == 0) *c.s_count = c.K;
         trigger = 0;
         __syncthreads();
-        thr = *c.s_thr;
-        thr_f = __uint_as_float((unsigned)(thr >> 32));
+        thr_f = __uint_as_float((unsigned)(*c.s_thr >> 32));
     }
 }
 
@@ -217,7 +230,7 @@ __global__ void __launch_bounds__(kThreads) decode_stream_kernel(const DecodePar
 
     StreamCtx c;
     c.ring = reinterpret_cast<float*>(smem_raw);
-    c.cand = reinterpret_cast<unsigned long long*>(c.ring + (size_t)kSlots * p.slot_floats);
+    c.cand = reinterpret_cast<unsigned long long*>(c.ring + (size_t)kSlots * kSlotFloats);
     c.keep = c.cand + p.cap;
     c.full_bar = full_bar;
     c.hist = hist;
@@ -242,7 +255,6 @@ __global__ void __launch_bounds__(kThreads) decode_stream_kernel(const DecodePar
     c.H = H;
     c.K = p.K;
     c.compact_at = p.compact_at;
-    c.slot_floats = p.slot_floats;
     c.row_floats = (px_hi - px_lo) * stride;
     c.row_floats_g = (long long)W * stride;
     const long long f_virtual = (((long long)b * H + (c.ra - 1)) * W + px_lo) * stride;   // may point before the tensor when ra == 0
@@ -265,7 +277,7 @@ __global__ void __launch_bounds__(kThreads) decode_stream_kernel(const DecodePar
         s_thr = 0ull;
     }
     if (tid < kSlots * 4)  // -inf sentinels behind the data of every slot: neighbours outside the image, idle columns
-        c.ring[(size_t)(tid >> 2) * p.slot_floats + p.slot_floats - 4 + (tid & 3)] = neg_inf();
+        c.ring[(size_t)(tid >> 2) * kSlotFloats + kSlotFloats - 4 + (tid & 3)] = neg_inf();
     __syncthreads();
 
     for (int r = r_first; r <= c.r_last && r < c.ra - 1 + kSlots; ++r) load_row(c, r, tid);
@@ -274,7 +286,7 @@ __global__ void __launch_bounds__(kThreads) decode_stream_kernel(const DecodePar
     const float* pv[kE];
     const float* pl[kE];
     const float* pr[kE];
-    const float* const sent = c.ring + p.slot_floats - 4;
+    const float* const sent = c.ring + kSlotFloats - 4;
 #pragma unroll
     for (int k = 0; k < kE; ++k) {
         const int e = tid + k * kThreads;
@@ -293,21 +305,23 @@ __global__ void __launch_bounds__(kThreads) decode_stream_kernel(const DecodePar
     for (int k = 0; k < kE; ++k) hA[k] = hB[k] = hC[k] = hD[k] = va[k] = vb[k] = neg_inf();
 
     uint32_t phase_bits = 0;
-    unsigned long long thr = 0ull;
     float thr_f = __uint_as_float(1u);  // smallest positive float: "score > 0" and "score >= threshold" in one compare
     int trigger = 0;                    // this thread received a buffer position at/after the compaction mark
 
-    // rows ra-1 .. rb.  Four h register sets rotate with period 4 (= ring depth, so the slot is a compile-time constant),
-    // the two value sets with period 2: no register moves between rows.
-#define CVM_STEP(J, HP, HC, HN, VC, VN)                                                                       \
-    if (r + J <= c.rb) row_step<J>(c, r + J, tid, pv, pl, pr, HP, HC, HN, VC, VN, phase_bits, thr, thr_f, trigger)
+    // rows ra-1 .. rb, two per barrier.  Four h register sets rotate with period 4 (= ring depth, so the slot is a
+    // compile-time constant), the two value sets with period 2: no register moves between rows.
+#define CVM_ROW(J, HP, HC, HN, VC, VN) \
+    row_compute<J>(c, r + J, pv, pl, pr, HP, HC, HN, VC, VN, phase_bits, thr_f, trigger)
     for (int r = c.ra - 1; r <= c.rb; r += 4) {
-        CVM_STEP(0, hC, hD, hA, vb, va);
-        CVM_STEP(1, hD, hA, hB, va, vb);
-        CVM_STEP(2, hA, hB, hC, vb, va);
-        CVM_STEP(3, hB, hC, hD, va, vb);
+        CVM_ROW(0, hC, hD, hA, vb, va);
+        if (r + 1 <= c.rb) CVM_ROW(1, hD, hA, hB, va, vb);
+        step_end(c, r, tid, thr_f, trigger);
+        if (r + 2 > c.rb) break;
+        CVM_ROW(2, hA, hB, hC, vb, va);
+        if (r + 3 <= c.rb) CVM_ROW(3, hB, hC, hD, va, vb);
+        step_end(c, r + 2, tid, thr_f, trigger);
     }
-#undef CVM_STEP
+#undef CVM_ROW
 
     int n = s_count;
     if (n > p.K) {
@@ -460,8 +474,10 @@ int plan_tiling(const cvm_layout* L, int stride, int B, int K, Tiling* t) {
     const int hm = L->hm, H = L->H, W = L->W;
     int tw_max = (kThreads * kE) / hm;
     if (tw_max < 1) return CVM_ERR_ARG;
-    // keep one ring slot <= 24 KB
-    while (tw_max > 8 && (size_t)(tw_max + 2) * stride * 4 > 24 * 1024) tw_max >>= 1;
+    // a row segment (band + 1-pixel halo each side + alignment slack + sentinels) must fit the fixed ring slot
+    const int tw_slot = (kSlotFloats - 12) / stride - 2;
+    if (tw_slot < 1) return CVM_ERR_ARG;
+    if (tw_max > tw_slot) tw_max = tw_slot;
     t->nbx = (W + tw_max - 1) / tw_max;
     t->TW = (W + t->nbx - 1) / t->nbx;
     // stripes: enough CTAs to fill the machine ~3x, but never so many that the merge needs more than 16K keys
@@ -474,9 +490,9 @@ int plan_tiling(const cvm_layout* L, int stride, int B, int K, Tiling* t) {
     if ((long long)nsy * t->nbx * K > 16384) return CVM_ERR_ARG;
     t->SR = (H + nsy - 1) / nsy;
     t->nsy = (H + t->SR - 1) / t->SR;
-    t->slot_floats = ((((t->TW + 2) * stride + 8) + 3) & ~3) + 4;   // + 4 sentinel floats
+    t->slot_floats = kSlotFloats;
     t->compact_at = K + kSlack;
-    t->cap = t->compact_at + t->TW * hm;
+    t->cap = t->compact_at + 2 * t->TW * hm;   // two rows of appends between barriers
     t->smem_stream = (size_t)kSlots * t->slot_floats * 4 + (size_t)t->cap * 8 + (size_t)K * 8;
     const int NT = t->nbx * t->nsy;
     t->smem_merge = ((size_t)NT * K + 2 * (size_t)K) * 8;

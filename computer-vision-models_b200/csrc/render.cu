@@ -18,6 +18,7 @@ namespace {
 
 constexpr int kThreads = 256;   // power of two: column ownership is x & (kThreads - 1)
 constexpr int kMaxObjSmem = 96;  // objects are processed in chunks of this many
+constexpr int kMaxIgnSmem = 16;  // ignore boxes cached in shared memory per band (more are read from global)
 
 struct RenderParams {
     const cvm_obj* objs;
@@ -101,7 +102,7 @@ __device__ __forceinline__ void derive(const cvm_obj& o, const RenderParams& p, 
     d.last_at_pixel = 1;
 }
 
-__global__ void __launch_bounds__(kThreads) render_kernel(const RenderParams p) {
+__global__ void __launch_bounds__(kThreads, 3) render_kernel(const RenderParams p) {
     extern __shared__ __align__(16) float planes[];  // [n_planes + 1][plane_stride]; last = weights
     __shared__ ObjDerived sobj[kMaxObjSmem];
     __shared__ int s_list[kMaxObjSmem];
@@ -126,18 +127,40 @@ __global__ void __launch_bounds__(kThreads) render_kernel(const RenderParams p) 
     }
 
     // compose mapping (vector path): the NHWC pattern repeats every 4 pixels = Cout float4s.  Thread t < NA handles float4
-    // slot r = t % Cout of pixel groups g = t / Cout, + GS, ...; which plane/pixel feeds its 4 floats never changes.
+    // slot r = t % Cout of pixel groups g = t / Cout, + GS, ...; which plane/pixel feeds its 4 floats never changes, so the
+    // loop is four shared loads through four pointers that advance by a fixed step (step 0 on a zero word for the
+    // channels that are always zero) and one 128-bit store.
+    __shared__ float s_zero[4];
+    if (tid < 4) s_zero[tid] = 0.f;
     const int GS = kThreads / Cout, NA = GS * Cout;
-    int coff[4] = {-1, -1, -1, -1};
-    const int cr = tid % Cout, cg0 = tid / Cout;
-    if (p.vec_ok && tid < NA) {
+    const int cg0 = tid / Cout;
+    const float* csrc[4];
+    int cinc[4];
+    {
+        const int cr = tid - cg0 * Cout;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int f = 4 * cr + k, pig = f / Cout, ch = f - pig * Cout;
-            if (ch < hm)
-                coff[k] = ch * PS + pig;
-            else if (ch == wch)
-                coff[k] = hm * PS + pig;
+            csrc[k] = s_zero;
+            cinc[k] = 0;
+            if (ch < hm || ch == wch) {
+                csrc[k] = planes + (ch < hm ? ch : hm) * PS + pig + 4 * cg0;
+                cinc[k] = 4 * GS;
+            }
+        }
+    }
+    // ignore boxes of this image, cached once per band (processor.py:318-323)
+    __shared__ int s_ign[kMaxIgnSmem][4];   // sx, ex, sy, ey (clamped)
+    int n_ign = 0, i_begin = 0;
+    if (p.ignore != nullptr && wch >= 0) {
+        i_begin = p.ign_offsets[b];
+        n_ign = p.ign_offsets[b + 1] - i_begin;
+        if (tid < min(n_ign, kMaxIgnSmem)) {
+            const cvm_box bx = p.ignore[i_begin + tid];
+            s_ign[tid][0] = max((int)bx.x, 0);
+            s_ign[tid][1] = min(max((int)(bx.x + bx.w), 0), W);
+            s_ign[tid][2] = max((int)bx.y, 0);
+            s_ign[tid][3] = min(max((int)(bx.y + bx.h), 0), p.H);
         }
     }
 
@@ -191,16 +214,18 @@ __global__ void __launch_bounds__(kThreads) render_kernel(const RenderParams p) 
         }
 
         // ---- ignore areas: weights = 0, input-px numbers used as mask indices (processor.py:318-323) ----
-        if (p.ignore != nullptr && wch >= 0) {
-            const int i_begin = p.ign_offsets[b], i_end = p.ign_offsets[b + 1];
-            for (int i = i_begin; i < i_end; ++i) {
-                const cvm_box bx = p.ignore[i];
-                const int sy = max((int)bx.y, 0), ey = min(max((int)(bx.y + bx.h), 0), p.H);
-                const int sx = max((int)bx.x, 0), ex = min(max((int)(bx.x + bx.w), 0), W);
-                const int r0 = max(sy, ya), r1 = min(ey, yb);
-                for (int x = sx + ((tid - sx) & (kThreads - 1)); x < ex; x += kThreads)   // same column ownership as the splat
-                    for (int y = r0; y < r1; ++y) wplane[(y - ya) * W + x] = 0.f;
+        for (int i = 0; i < n_ign; ++i) {
+            int sx, ex, sy, ey;
+            if (i < kMaxIgnSmem) {
+                sx = s_ign[i][0], ex = s_ign[i][1], sy = s_ign[i][2], ey = s_ign[i][3];
+            } else {
+                const cvm_box bx = p.ignore[i_begin + i];
+                sx = max((int)bx.x, 0), ex = min(max((int)(bx.x + bx.w), 0), W);
+                sy = max((int)bx.y, 0), ey = min(max((int)(bx.y + bx.h), 0), p.H);
             }
+            const int r0 = max(sy, ya), r1 = min(ey, yb);
+            for (int x = sx + ((tid - sx) & (kThreads - 1)); x < ex; x += kThreads)   // same column ownership as the splat
+                for (int y = r0; y < r1; ++y) wplane[(y - ya) * W + x] = 0.f;
         }
         __syncthreads();
 
@@ -211,14 +236,13 @@ __global__ void __launch_bounds__(kThreads) render_kernel(const RenderParams p) 
             if (tid < NA) {
                 const int n_groups = (nrows * W) >> 2;
                 float4* dst = reinterpret_cast<float4*>(out_tile) + tid;
+                const float *s0 = csrc[0], *s1 = csrc[1], *s2 = csrc[2], *s3 = csrc[3];
                 for (int g = cg0; g < n_groups; g += GS, dst += NA) {
-                    const int g4 = g << 2;
-                    float4 v;
-                    v.x = coff[0] >= 0 ? planes[coff[0] + g4] : 0.f;
-                    v.y = coff[1] >= 0 ? planes[coff[1] + g4] : 0.f;
-                    v.z = coff[2] >= 0 ? planes[coff[2] + g4] : 0.f;
-                    v.w = coff[3] >= 0 ? planes[coff[3] + g4] : 0.f;
-                    st_cs_f4(dst, v);
+                    st_cs_f4(dst, make_float4(*s0, *s1, *s2, *s3));
+                    s0 += cinc[0];
+                    s1 += cinc[1];
+                    s2 += cinc[2];
+                    s3 += cinc[3];
                 }
             }
         } else {
