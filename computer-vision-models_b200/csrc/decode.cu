@@ -4,63 +4,146 @@
 //
 // Bound: HBM reads.  Algorithmic bytes per image: 4*H*W*pred_stride, read exactly once.
 //
-// Kernel 1 (decode_stream_kernel): one CTA per (image, row stripe, column band).  Thread 0 streams the band's row
-// segments through a shared-memory ring with 1-D bulk async copies (UBLKCP + mbarrier); every thread owns E fixed
-// (x, channel) element-columns and walks down the rows keeping the 3-tap horizontal maxima of the two previous rows in
-// registers, so the 3x3 test costs 3 shared loads per element.  Survivors are turned into 64-bit keys
-// (score bits << 32 | ~flat index): a total order with no ties, equal to (score desc, flat index asc).  Keys above the
-// CTA's running threshold are appended to a shared-memory buffer; when it fills up an exact radix select (256-bin shared
-// histogram per byte, warp-level suffix scan) keeps the best K and raises the threshold.  y_pred is never re-read.
-// Kernel 2 (decode_merge_kernel): one CTA per image merges the <= K keys of each tile (same radix select), rank-sorts the
-// K winners, fills a short tail with score-0 entries in flat-index order (tf.nn.top_k semantics on the masked map),
-// gathers r_offset / fullbox / track_offset at the peaks and assembles boxes.
+// Kernel 1 (decode_scan_kernel).  The batch is one flat list of steps (T = 480 consecutive pixels of one image, all
+// channels: a contiguous piece of y_pred).  The list is cut into gridDim.x equal contiguous ranges, one persistent CTA
+// per SM and range, so every SM streams the same number of bytes.  A loader warp feeds a shared-memory ring of granules
+// (Pg pixels each) with 1-D bulk async copies (TMA engine: UBLKCP + mbarrier, full/empty barrier pair per slot),
+// several granules ahead.  Fifteen scanner warps walk the steps WITHOUT any CTA-wide barrier: per step every lane owns
+// one pixel, takes the maximum over the heatmap channels (vector shared loads, no bank conflicts) and compares it ONCE
+// with the CTA's running threshold score.  A lane whose pixel reaches the threshold tests it one step later, when the
+// pixels after it have arrived: the 3x3 test reads the eight neighbours out of the ring (W + 1 pixels of history and
+// lookahead stay resident; for maps too wide for that they are read from global memory).  Peaks are appended to a
+// shared-memory candidate buffer as 64-bit keys (score bits << 32 | ~flat index): a total order with no ties, equal
+// to (score desc, flat index asc).  A score histogram of the appended peaks raises the threshold (one warp scans it
+// between steps).  Only two rare events gather the scanner warps on a named barrier: the buffer passing its mark (exact
+// radix select, keeps the best K) and the end of an image, where the CTA writes its <= K best keys of that image
+// ("segment") to the workspace and starts over.
+// Kernel 2 (decode_merge_kernel): one CTA per image merges the segments of the CTAs that touched it (same radix select),
+// rank-sorts the K winners, fills a short tail with score-0 entries in flat-index order (tf.nn.top_k semantics on the
+// masked map), gathers r_offset / fullbox / track_offset at the peaks and assembles boxes.
+#include <limits.h>
 #include <stdlib.h>
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kSlots = 4;         // row-segment ring depth (2 rows consumed per step while 2 are in flight; deeper rings cost occupancy and measured slower)
-constexpr int kSlack = 1024;      // buffer entries beyond K before the (rare) fallback compaction
-constexpr int kScoreBins = 2048;  // score histogram: bin = float bits >> 20 (sign 0, 8 exponent bits, 3 mantissa bits)
+constexpr int kScanThreads = 480;  // scanner threads: one pixel per thread and step (15 warps + the loader warp = 4 warps per
+                                   // SM sub-partition, which leaves 128 registers per thread; a 17th warp caps them at 96 and spills)
+constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kThreads = kScanThreads + 32;   // + the loader warp
+constexpr int kMergeThreads = 256;
+constexpr int kMaxSlots = 32;      // ring depth (granules) the barrier arrays can hold
+constexpr int kSlack = 2048;       // buffer entries beyond K before the (rare) fallback compaction
+constexpr int kSegKeys = 512;      // keys a segment may publish without an exact select (the merge kernel selects anyway)
+constexpr int kScoreShift = 19;    // score histogram: bin = float bits >> 19 (sign 0, 8 exponent bits, 4 mantissa bits)
+constexpr int kScoreBins = 1 << (31 - kScoreShift);
 constexpr int kMaxK = 1024;
-// Two instantiations of the streaming kernel: <5, 2112> (narrow bands, ~80 registers, 3-4 CTAs/SM: the fast one) and
-// <8, 3328> (wide pixel strides).  KE = element-columns per thread, SLOTF = floats per ring slot (compile-time so that
-// slot offsets are immediates).
+constexpr int kMaxAppend = 5120;   // T * hm: most candidates one step can append between two barriers
+constexpr int kMergeCap = 4096;    // merge kernel: keys buffered before an intermediate select
+constexpr int kSmemBudget = 227 * 1024 - 1024;
 
 struct DecodeParams {
     const float* yp;
-    long long total_floats;       // B*H*W*stride
     int stride, H, W, hm, K;
-    int TW, nbx;                  // band width, bands per row
-    int n_big, m_small, SR_small; // columns [0, n_big) are one tall tile each; the others are cut into m_small stripes
-    int slot_floats;              // floats per ring slot (multiple of 4)
+    int HW;                       // pixels per image
+    int T;                        // pixels per step = pixels per ring granule (<= kScanThreads)
+    int spi;                      // steps (= granules) per image
+    long long n_steps;            // B * spi
+    int S;                        // ring slots (granules)
+    int ring_nb;                  // 1: neighbours are read from the ring; 0: from global memory
+    int halo_g;                   // granules of history / lookahead that hold W + 1 pixels (0 without ring_nb)
+    int gran_floats;              // T * stride
     int cap;                      // candidate buffer entries
-    int compact_at;               // compact when more than this many candidates are buffered
-    int use_bulk;
-    float inv_hm;
-    unsigned long long* keys;     // [n_tiles][K], tile = blockIdx.x
-    int* counts;                  // [n_tiles]
+    int compact_at;               // compact when a candidate lands at or beyond this position
+    int max_segs;                 // images one CTA range can touch
+    int seg_keys;                 // keys a segment can publish (>= K)
+    unsigned long long* keys;     // [grid][max_segs][seg_keys]
+    int* counts;                  // [grid][max_segs]
+    unsigned int thr0_bits;       // initial threshold score bits (1 = smallest positive float; experiments only raise it)
+    float inv_W;                  // 1 / W
 };
 
-__device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
+// Fixed-size head of the dynamic shared memory block; the ring, the candidate buffer, the select scratch and the score
+// histogram follow (see smem_layout()).
+struct SharedHead {
+    uint64_t full_bar[kMaxSlots];   // loader -> scanners: granule arrived (tx bytes, or a plain arrive without the bulk engine)
+    uint64_t empty_bar[kMaxSlots];  // scanners -> loader: all scanner warps are done with the granule
+    unsigned int hist[256];       // radix select
+    int misc[4];
+    // control word, read by every scanner warp once per step with ONE 64-bit shared load (a warp-wide broadcast, so
+    // all lanes of a warp always see the same pair)
+    unsigned int thr_bits;        // running threshold score (float bits), raised by the histogram scan
+    int compact_flag;             // an append landed at/after the compaction mark
+    int count;                    // candidates buffered
+    int scanned;                  // `count` when the histogram was last scanned
+    int maxbin;                   // highest score bin seen so far
+    int seg_done;                 // scanner warps that finished the current segment
+    unsigned long long thr;       // K-th key of the last exact select
+#ifdef CVM_WATCHDOG
+    int dbg_state[16];
+#endif
+};
+constexpr int kHeadBytes = (sizeof(SharedHead) + 127) & ~127;
+
+// The dynamic shared memory block, declared at file scope so that every device function addresses it in the shared
+// state space (LDS/STS/ATOMS); passing views of it through structs or pointers degrades them to generic accesses.
+extern __shared__ __align__(128) unsigned char g_smem[];
+
+__device__ __forceinline__ SharedHead* sm_head() { return reinterpret_cast<SharedHead*>(g_smem); }
+#ifdef CVM_WATCHDOG
+__device__ __forceinline__ int* sm_head_raw();
+#endif
+#ifdef CVM_WATCHDOG
+__device__ __forceinline__ int* sm_head_raw() { return sm_head()->dbg_state; }
+#endif
+// [S][gran_floats] (+ 4 floats of slack for vector over-reads of the last pixel)
+__device__ __forceinline__ float* sm_ring() { return reinterpret_cast<float*>(g_smem + kHeadBytes); }
+// [cap] candidate keys
+__device__ __forceinline__ unsigned long long* sm_cand(const DecodeParams& p) {
+    return reinterpret_cast<unsigned long long*>(g_smem + kHeadBytes + ((size_t)p.S * p.gran_floats + 4) * 4);
+}
+// [K] select scratch
+__device__ __forceinline__ unsigned long long* sm_keep(const DecodeParams& p) { return sm_cand(p) + p.cap; }
+// [kScoreBins] score histogram of the buffered candidates
+__device__ __forceinline__ unsigned int* sm_shist(const DecodeParams& p) {
+    return reinterpret_cast<unsigned int*>(sm_keep(p) + p.K);
+}
+
+size_t smem_bytes(int S, int gran_floats, int cap, int K) {
+    return (size_t)kHeadBytes + ((size_t)S * gran_floats + 4) * 4 + (size_t)cap * 8 + (size_t)K * 8 + (size_t)kScoreBins * 4;
+}
+
+#ifdef CVM_WATCHDOG
+#define DBG_STATE(code) do { if ((threadIdx.x & 31) == 0) ((volatile int*)sm_head_raw())[threadIdx.x >> 5] = (code); } while (0)
+#else
+#define DBG_STATE(code) do { } while (0)
+#endif
+
+// named barrier over the first `nt` threads of the CTA (the scanner warps; the loader warp never joins)
+__device__ __forceinline__ void group_sync(int nt) { asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory"); }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 
 // ---- exact top-K select on distinct 64-bit keys held in shared memory -------------------------------------------------
-// On return keys[0..K) hold the K largest (unordered), *thr is the K-th largest key.  n > K required.  All threads call.
+// On return keys[0..K) hold the K largest (unordered), *thr is the K-th largest key.  n > K required.  Called by the
+// first nt threads of the CTA.
 __device__ __noinline__ void select_topk(unsigned long long* keys, int n, int K, unsigned int* hist, unsigned long long* keep,
-                            int* s_misc /* [4] */, unsigned long long* thr_out) {
+                                         int* s_misc /* [4] */, unsigned long long* thr_out, int nt) {
     const int tid = threadIdx.x;
     unsigned long long prefix = 0ull, mask = 0ull;
     int need = K;
     for (int shift = 56; shift >= 0; shift -= 8) {
-        hist[tid] = 0;  // kThreads == 256 bins
-        __syncthreads();
-        for (int i = tid; i < n; i += kThreads) {
+        if (tid < 256) hist[tid] = 0;
+        group_sync(nt);
+        for (int i = tid; i < n; i += nt) {
             const unsigned long long k = keys[i];
             if ((k & mask) == prefix) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
         }
-        __syncthreads();
+        group_sync(nt);
         if (tid < 32) {
             // lane l owns bins [255-8l-7, 255-8l], scanned from the top
             unsigned int loc[8], sum = 0;
@@ -88,137 +171,43 @@ __device__ __noinline__ void select_topk(unsigned long long* keys, int n, int K,
                 }
             }
         }
-        __syncthreads();
+        group_sync(nt);
         const int digit = s_misc[0];
         need = s_misc[1];
         const int pop = s_misc[2];
         prefix |= (unsigned long long)digit << shift;
         mask |= 0xFFull << shift;
-        __syncthreads();  // s_misc is rewritten next pass
+        group_sync(nt);  // s_misc is rewritten next pass
         if (pop == need) break;  // the whole bin is selected: every key >= prefix (low bits zero) is kept
     }
     const unsigned long long T = prefix;
     if (tid == 0) s_misc[3] = 0;
-    __syncthreads();
-    for (int i = tid; i < n; i += kThreads) {
+    group_sync(nt);
+    for (int i = tid; i < n; i += nt) {
         const unsigned long long k = keys[i];
         if (k >= T) keep[atomicAdd(&s_misc[3], 1)] = k;
     }
-    __syncthreads();
-    for (int i = tid; i < K; i += kThreads) keys[i] = keep[i];
+    group_sync(nt);
+    for (int i = tid; i < K; i += nt) keys[i] = keep[i];
     // T is the K-th largest key with (after an early exit) its undecided low bits zeroed: a valid, at most marginally
     // weaker, lower bound for every later candidate
     if (tid == 0) *thr_out = T;
-    __syncthreads();
+    group_sync(nt);
 }
 
-// Everything the per-row step needs that is not per-thread register state.
-struct StreamCtx {
-    float* ring;
-    unsigned long long* cand;
-    unsigned long long* keep;
-    uint64_t* full_bar;
-    unsigned int* hist;
-    int* s_misc;
-    int* s_count;
-    unsigned long long* s_thr;
-    unsigned int* shist;      // [kScoreBins] counts of buffered candidates per score bin (top 11 bits of the score)
-    unsigned int* s_thr_bits; // running threshold score (float bits), raised by the histogram scan
-    int* s_scanned;           // *s_count when the histogram was last scanned
-    int* s_maxbin;            // highest score bin seen so far
-    const float* gsrc;        // global address of (row ra-1, pixel px_lo, channel 0) (virtual when ra == 0)
-    long long row_floats_g;   // W * stride
-    int row_floats;           // (px_hi - px_lo) * stride
-    int lead;                 // data of a row starts `lead` floats into its slot (16-byte granularity of the bulk copy)
-    int r_last, ra, rb, H, K, compact_at, bulk;
-    unsigned flat_x0, flat_row_step;
-};
-
-// global -> ring slot (row r lives in slot (r - (ra-1)) & 3): thread 0 with the bulk engine, or everybody with plain loads
-template <int SLOTF, bool BULK>
-__device__ __forceinline__ void load_row(const StreamCtx& c, int r, int tid) {
-    const int i = r - (c.ra - 1), s = i & (kSlots - 1);
-    float* dst = c.ring + (size_t)s * SLOTF;
-    if (BULK) {
-        if (tid == 0) {
-            const float* src = c.gsrc + (long long)i * c.row_floats_g;   // first needed float
-            const uint32_t bytes = (uint32_t)(((c.lead + c.row_floats + 3) & ~3) * 4);
-            mbar_arrive_expect_tx(&c.full_bar[s], bytes);
-            bulk_g2s(dst, src - c.lead, bytes, &c.full_bar[s]);
-        }
-    } else {
-        const float* src = c.gsrc + (long long)i * c.row_floats_g;
-        for (int j = tid; j < c.row_floats; j += kThreads) dst[c.lead + j] = src[j];
-    }
-}
-
-// One row: bring row r's values / 3-tap maxima into (vn, hn), then test row r-1 with (hp, hc, hn, vc).
-// SLOT (= step index mod 4) and the slot size are compile-time constants: every shared load is [register + immediate].
-template <int SLOT, int KE, int SLOTF, bool BULK>
-__device__ __forceinline__ void row_compute(const StreamCtx& c, int r, const float* const (&pv)[KE],
-                                            const float* const (&pl)[KE], const float* const (&pr)[KE],
-                                            const float (&hp)[KE], const float (&hc)[KE], float (&hn)[KE],
-                                            const float (&vc)[KE], float (&vn)[KE], uint32_t& phase_bits, float thr_f,
-                                            int& trigger) {
-    if (BULK) {
-        mbar_wait(&c.full_bar[SLOT], (phase_bits >> SLOT) & 1u);
-        phase_bits ^= 1u << SLOT;
-    } else {
-        __syncthreads();
-    }
-    constexpr int so = SLOT * SLOTF;
-#pragma unroll
-    for (int k = 0; k < KE; ++k) {
-        const float v = pv[k][so];
-        vn[k] = v;
-        hn[k] = fmaxf(v, fmaxf(pl[k][so], pr[k][so]));
-    }
-    const int yt = r - 1;  // row whose 3x3 neighbourhood is now complete
-    if (yt >= c.ra && yt < c.rb) {
-        // hot path: ONE compare per thread and row against the running threshold score (positive by construction); only
-        // threads holding a value that could still make the top K pay for the 3x3 tests.
-        float vmax = vc[0];
-#pragma unroll
-        for (int k = 1; k < KE; ++k) vmax = fmaxf(vmax, vc[k]);
-        if (vmax >= thr_f) {
-            const unsigned flat_row = (unsigned)yt * c.flat_row_step + c.flat_x0;
-            const unsigned cnt_addr = smem_u32(c.s_count), cand_addr = smem_u32(c.cand), hist_addr = smem_u32(c.shist);
-#pragma unroll
-            for (int k = 0; k < KE; ++k) {
-                // peak (value equals its 3x3 max) and not below the threshold score.  Scores equal to the threshold score
-                // are appended without looking at the index half of the key: the next select drops them.
-                if (vc[k] >= fmaxf(fmaxf(hp[k], hc[k]), fmaxf(hn[k], thr_f))) {
-                    // a plain (not warp-aggregated) shared atomic: candidates are sparse, a short divergent path matters more
-                    unsigned pos;
-                    asm volatile("atom.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(pos) : "r"(cnt_addr) : "memory");
-                    const unsigned flat = flat_row + (unsigned)(k * kThreads);
-                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(cand_addr + pos * 8u), "r"(0xFFFFFFFFu - flat),
-                                 "r"(__float_as_uint(vc[k]))
-                                 : "memory");
-                    trigger |= (pos >= (unsigned)c.compact_at);
-                    // score histogram (exact for every bin at or above the running threshold): feeds the threshold scan
-                    const unsigned bin = __float_as_uint(vc[k]) >> 20;
-                    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + bin * 4u) : "memory");
-                    if ((int)bin > *(volatile int*)c.s_maxbin) atomicMax(c.s_maxbin, (int)bin);
-                }
-            }
-        }
-    }
-}
-
-// Threshold scan (one warp): the largest score bin tb with at least K buffered candidates in bins >= tb.  Bins at or above
-// the running threshold are exact (everything that scores there was appended), so every later candidate below the
-// lower edge of tb cannot make the top K: the edge becomes the new threshold.  No buffer traffic, no CTA-wide sync.
-__device__ __noinline__ void scan_threshold(const unsigned int* shist, const int* s_count, int* s_scanned, const int* s_maxbin,
-                                            unsigned int* s_thr_bits, int K, int lane) {
-    const int n = *(volatile const int*)s_count;
-    if (n == *s_scanned || n < K) return;
-    const int top = *(volatile const int*)s_maxbin;
+// Threshold scan (one warp): the largest score bin tb with at least K buffered candidates in bins >= tb.  Every counted
+// entry is a real peak of this image, so a later candidate below the lower edge of tb cannot make the top K: the edge
+// becomes the new threshold.  Counts read while other warps append are at worst too low, which only makes the bound
+// conservative.  No buffer traffic, no CTA-wide sync.
+__device__ __noinline__ void scan_threshold(SharedHead* h, const unsigned int* shist, int K, int lane) {
+    const int n = *(volatile const int*)&h->count;
+    if (n == h->scanned || n < K) return;
+    const int top = *(volatile const int*)&h->maxbin;
     unsigned above = 0;
     for (int base = top; base >= 0; base -= 32) {
         const int bin = base - lane;
-        const unsigned h = bin >= 0 ? shist[bin] : 0u;
-        unsigned incl = h;
+        const unsigned v = bin >= 0 ? ((volatile const unsigned int*)shist)[bin] : 0u;
+        unsigned incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -228,211 +217,483 @@ __device__ __noinline__ void scan_threshold(const unsigned int* shist, const int
         if (hit) {
             const int tb = base - (__ffs(hit) - 1);
             if (lane == 0) {
-                const unsigned bits = (unsigned)tb << 20;
-                if (bits > *s_thr_bits) *s_thr_bits = bits;
-                *s_scanned = n;
+                const unsigned bits = (unsigned)tb << kScoreShift;
+                if (bits > h->thr_bits) h->thr_bits = bits;
+                h->scanned = n;
             }
             return;
         }
         above += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (lane == 0) *s_scanned = n;
+    if (lane == 0) h->scanned = n;
+}
+
+// Sum of `v` over the first nt threads of the CTA (one shared atomic per warp); `slot` is scratch.
+__device__ __forceinline__ int __syncthreads_count_scan(int v, int nt, int* slot) {
+    if (threadIdx.x == 0) *slot = 0;
+    group_sync(nt);
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(slot, v);
+    group_sync(nt);
+    const int total = *(volatile int*)slot;
+    group_sync(nt);
+    return total;
 }
 
 // Fallback when the candidate buffer passed the mark: exact select, then the histogram is rebuilt from the K survivors.
-__device__ __noinline__ void compact_buffer(unsigned long long* cand, int* s_count, int K, unsigned int* hist,
-                                            unsigned long long* keep, int* s_misc, unsigned long long* s_thr,
-                                            unsigned int* shist, int* s_scanned, unsigned int* s_thr_bits) {
-    const int tid = threadIdx.x;
-    select_topk(cand, *s_count, K, hist, keep, s_misc, s_thr);
-    for (int i = tid; i < kScoreBins; i += kThreads) shist[i] = 0u;
-    __syncthreads();
-    for (int i = tid; i < K; i += kThreads) atomicAdd(&shist[(unsigned)(cand[i] >> 52)], 1u);
+__device__ __noinline__ void compact_buffer(const DecodeParams& p) {
+    const int tid = threadIdx.x, nt = kScanThreads, K = p.K;
+    SharedHead* h = sm_head();
+    unsigned long long* cand = sm_cand(p);
+    unsigned int* shist = sm_shist(p);
+    select_topk(cand, h->count, K, h->hist, sm_keep(p), h->misc, &h->thr, nt);
+    for (int i = tid; i < kScoreBins; i += nt) shist[i] = 0u;
+    group_sync(nt);
+    for (int i = tid; i < K; i += nt) atomicAdd(&shist[(unsigned)(cand[i] >> (32 + kScoreShift))], 1u);
     if (tid == 0) {
-        *s_count = K;
-        *s_scanned = K;
-        const unsigned bits = (unsigned)(*s_thr >> 32) & 0xFFF00000u;
-        if (bits > *s_thr_bits) *s_thr_bits = bits;
+        h->count = K;
+        h->scanned = K;
+        const unsigned bits = (unsigned)(h->thr >> 32) & ~((1u << kScoreShift) - 1u);
+        if (bits > h->thr_bits) h->thr_bits = bits;
+        h->compact_flag = 0;
     }
-    __syncthreads();
+    group_sync(nt);
 }
 
-// A bottom stripe ends with the virtual row H: its ring slot is filled with -inf and its barrier completed by hand, so
-// the hot loop needs no special case.
-template <int SLOTF, bool BULK>
-__device__ __noinline__ void fill_virtual_row(float* ring, uint64_t* full_bar, int slot) {
-    float* dst = ring + (size_t)slot * SLOTF;
-    for (int j = threadIdx.x; j < SLOTF; j += kThreads) dst[j] = neg_inf();
-    __syncthreads();
-    if (BULK && threadIdx.x == 0) mbar_arrive_expect_tx(&full_bar[slot], 0);
-}
-
-// End of a step of two rows: release the two slots, refill them, raise the threshold from the score histogram; compact
-// the candidate buffer only if it passed the mark (rare: the histogram threshold keeps the buffer short).
-template <int SLOTF, bool BULK>
-__device__ __forceinline__ void step_end(const StreamCtx& c, int r, int tid, float& thr_f, int& trigger) {
-    // slots consumed by everyone; appends of these rows are visible.  The OR of the per-thread marks is the only race-free
-    // uniform way to learn "buffer passed the mark" (fast threads may already append for the next rows once they leave
-    // a plain barrier, so *s_count itself must not be sampled here).
-    const int do_compact = __syncthreads_or(trigger);
-    thr_f = __uint_as_float(*(volatile unsigned int*)c.s_thr_bits);   // written during the previous step: one step stale, still valid
-    // refill with the rows kSlots ahead (also after the virtual row -1 of a top stripe, whose slot is idle)
-#pragma unroll
-    for (int d = 0; d < 2; ++d) {
-        const int rr = r + d + kSlots;
-        if (rr >= 0 && rr <= c.r_last)
-            load_row<SLOTF, BULK>(c, rr, tid);
-        else if (rr == c.H && c.rb == c.H)
-            fill_virtual_row<SLOTF, BULK>(c.ring, c.full_bar, (rr - (c.ra - 1)) & (kSlots - 1));
-    }
-    if (do_compact) {  // every thread is in here, so *s_count is frozen
-        compact_buffer(c.cand, c.s_count, c.K, c.hist, c.keep, c.s_misc, c.s_thr, c.shist, c.s_scanned, c.s_thr_bits);
-        trigger = 0;
-        thr_f = __uint_as_float(*(volatile unsigned int*)c.s_thr_bits);
-    } else if ((tid >> 5) == 1) {
-        scan_threshold(c.shist, c.s_count, c.s_scanned, c.s_maxbin, c.s_thr_bits, c.K, tid & 31);
-    }
-}
-
-template <int KE, int SLOTF, int MIN_CTAS, bool BULK>
-__global__ void __launch_bounds__(kThreads, MIN_CTAS) decode_stream_kernel(const DecodeParams p) {
-    static_assert(kSlots == 4, "the row loop below is unrolled over the 4 ring slots");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t full_bar[kSlots];
-    __shared__ unsigned int hist[256];
-    __shared__ int s_misc[4];
-    __shared__ int s_count;
-    __shared__ unsigned long long s_thr;
-    __shared__ unsigned int s_thr_bits;
-    __shared__ int s_scanned, s_maxbin;
-
-    StreamCtx c;
-    c.ring = reinterpret_cast<float*>(smem_raw);
-    c.cand = reinterpret_cast<unsigned long long*>(c.ring + (size_t)kSlots * SLOTF);
-    c.keep = c.cand + p.cap;
-    c.shist = reinterpret_cast<unsigned int*>(c.keep + p.K);
-    c.s_thr_bits = &s_thr_bits;
-    c.s_scanned = &s_scanned;
-    c.s_maxbin = &s_maxbin;
-    c.full_bar = full_bar;
-    c.hist = hist;
-    c.s_misc = s_misc;
-    c.s_count = &s_count;
-    c.s_thr = &s_thr;
-
-    const int tid = threadIdx.x;
-    // tile geometry.  "Column" = (image, band).  The first n_big columns are processed top to bottom by one CTA each
-    // (longest tiles first); the remaining ones are cut into m_small stripes so that the tail of the grid balances.
-    int col, ra0, rb0;
-    if ((int)blockIdx.x < p.n_big) {
-        col = blockIdx.x;
-        ra0 = 0;
-        rb0 = p.H;
+// End of a (CTA, image) segment: publish the candidates that still reach the running threshold (the merge kernel does
+// the exact select; only a segment with more than kSegKeys of them selects its best K first), reset the selection
+// state.  All scanner threads, count frozen.
+__device__ __noinline__ void flush_segment(const DecodeParams& p, int seg) {
+    const int tid = threadIdx.x, nt = kScanThreads;
+    SharedHead* h = sm_head();
+    unsigned long long* cand = sm_cand(p);
+    unsigned int* shist = sm_shist(p);
+    const size_t o = (size_t)blockIdx.x * p.max_segs + seg;
+    unsigned long long* out = p.keys + o * p.seg_keys;
+    int n = h->count;
+    const unsigned thr_bits = h->thr_bits;
+    int above = 0;
+    for (int i = tid; i < n; i += nt) above += (unsigned)(cand[i] >> 32) >= thr_bits;
+    above = __syncthreads_count_scan(above, nt, &h->misc[0]);
+    if (above > p.seg_keys) {   // rare: heavy ties at the threshold score
+        select_topk(cand, n, p.K, h->hist, sm_keep(p), h->misc, &h->thr, nt);
+        n = p.K;
+        for (int i = tid; i < n; i += nt) out[i] = cand[i];
     } else {
-        const int q = blockIdx.x - p.n_big;
-        col = p.n_big + q / p.m_small;
-        ra0 = (q % p.m_small) * p.SR_small;
-        rb0 = min(p.H, ra0 + p.SR_small);
+        if (tid == 0) h->misc[1] = 0;
+        group_sync(nt);
+        for (int i = tid; i < n; i += nt) {
+            const unsigned long long k = cand[i];
+            if ((unsigned)(k >> 32) >= thr_bits) out[atomicAdd(&h->misc[1], 1)] = k;
+        }
+        n = above;
     }
-    const int b = col / p.nbx, bx = col - b * p.nbx;
-
-    const int H = p.H, W = p.W, hm = p.hm, stride = p.stride;
-    const int xa = bx * p.TW, xb = min(W, xa + p.TW);
-    const int px_lo = max(xa - 1, 0), px_hi = min(xb + 1, W);
-    c.ra = ra0;
-    c.rb = rb0;
-    const int r_first = max(c.ra - 1, 0);
-    c.r_last = min(c.rb, H - 1);
-    c.H = H;
-    c.K = p.K;
-    c.compact_at = p.compact_at;
-    c.row_floats = (px_hi - px_lo) * stride;
-    c.row_floats_g = (long long)W * stride;
-    const long long f_virtual = (((long long)b * H + (c.ra - 1)) * W + px_lo) * stride;   // may point before the tensor when ra == 0
-    c.gsrc = p.yp + f_virtual;
-    c.lead = (int)((f_virtual + (c.ra == 0 ? c.row_floats_g : 0)) & 3LL);
-    c.flat_x0 = (unsigned)(xa * hm + tid);
-    c.flat_row_step = (unsigned)(W * hm);
-    c.bulk = BULK;
-    const int n_elem = (xb - xa) * hm;
-
+    for (int i = tid; i < kScoreBins; i += nt) shist[i] = 0u;
+    group_sync(nt);
     if (tid == 0) {
-        for (int s = 0; s < kSlots; ++s) mbar_init(&full_bar[s], 1);
-        mbar_fence_init();
-        s_count = 0;
-        s_thr = 0ull;
-        s_thr_bits = 1u;   // smallest positive float: "score > 0" and "score >= threshold" in one compare
-        s_scanned = 0;
-        s_maxbin = 0;
+        p.counts[o] = n;
+        h->count = 0;
+        h->thr = 0ull;
+        h->thr_bits = p.thr0_bits;
+        h->scanned = 0;
+        h->maxbin = 0;
+        h->compact_flag = 0;
+        h->seg_done = 0;
     }
-    for (int i = tid; i < kScoreBins; i += kThreads) c.shist[i] = 0u;
-    if (tid < kSlots * 4)  // -inf sentinels behind the data of every slot: neighbours outside the image, idle columns
-        c.ring[(size_t)(tid >> 2) * SLOTF + SLOTF - 4 + (tid & 3)] = neg_inf();
-    __syncthreads();
+    group_sync(nt);
+}
 
-    for (int r = r_first; r < c.ra - 1 + kSlots; ++r) {
-        if (r <= c.r_last)
-            load_row<SLOTF, BULK>(c, r, tid);
-        else if (r == H && c.rb == H)
-            fill_virtual_row<SLOTF, BULK>(c.ring, full_bar, (r - (c.ra - 1)) & (kSlots - 1));
-    }
+// One lane's pixel that reached the threshold and waits for its 3x3 test.
+struct Hit {
+    unsigned long long mask;   // heatmap channels whose score reached the threshold (0: no hit)
+    int q;                     // pixel index inside the image
+    int rp;                    // ring position (in pixels) of the pixel
+};
 
-    // fixed element-columns of this thread: addresses (inside slot 0) of the value and of its two x-neighbours
-    const float* pv[KE];
-    const float* pl[KE];
-    const float* pr[KE];
-    const float* const sent = c.ring + SLOTF - 4;
+// Exact 3x3 test of the pending hits of a warp and append of the peaks.  Called by ALL lanes of the warp (lanes without
+// a hit pass mask 0): the loop runs over the union of the lanes' channel masks, so votes and the aggregated append (one
+// shared atomic per warp and channel) are warp-uniform.  img: image of the pixels.
+__device__ __forceinline__ void test_hits(const DecodeParams& p, long long img, const Hit& hit, float thr_f) {
+    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)hit.mask);
+    const unsigned hi = p.hm > 32 ? __reduce_or_sync(0xffffffffu, (unsigned)(hit.mask >> 32)) : 0u;
+    unsigned long long uni = ((unsigned long long)hi << 32) | lo;
+    if (uni == 0ull) return;
+    SharedHead* h = sm_head();
+    const float* ring = sm_ring();
+    unsigned long long* cand = sm_cand(p);
+    unsigned int* shist = sm_shist(p);
+    const int lane = threadIdx.x & 31;
+    const int W = p.W, stride = p.stride, ring_px = p.S * p.T;
+    // channel 0 of the eight neighbours as an offset (in floats) into the ring (W + 1 pixels of halo are resident) or
+    // relative to this pixel in global memory; INT_MIN outside the map.  Interior pixels whose neighbourhood does not
+    // wrap around the ring (almost all) take the short way.
+    int nb[8];
+    const float* g_px = p.yp;
+    if (hit.mask) {
+        // y = q / W without an integer division (exact after one correction step for any q < 2^31)
+        const int q = hit.q;
+        int y = __float2int_rz(__fmul_rn((float)q, p.inv_W)), x = q - y * W;
+        if (x < 0) {
+            --y;
+            x += W;
+        } else if (x >= W) {
+            ++y;
+            x -= W;
+        }
+        g_px += ((size_t)img * p.HW + (size_t)q) * stride;
+        const bool interior = y > 0 && y < p.H - 1 && x > 0 && x < W - 1;
+        const bool flat = !p.ring_nb || (hit.rp - W - 1 >= 0 && hit.rp + W + 1 < ring_px);
+        if (interior && flat) {
+            const int base = p.ring_nb ? hit.rp * stride : 0;
 #pragma unroll
-    for (int k = 0; k < KE; ++k) {
-        const int e = tid + k * kThreads;
-        pv[k] = pl[k] = pr[k] = sent;
-        if (e < n_elem) {
-            const int xl = hm == 1 ? e : __float2int_rz(((float)e + 0.5f) * p.inv_hm);
-            const int ch = e - xl * hm;
-            const int x = xa + xl;
-            pv[k] = c.ring + c.lead + (x - px_lo) * stride + ch;
-            if (x > 0) pl[k] = pv[k] - stride;
-            if (x < W - 1) pr[k] = pv[k] + stride;
+            for (int k = 0; k < 8; ++k) {
+                const int j = k < 4 ? k : k + 1;
+                nb[k] = base + ((j / 3 - 1) * W + (j % 3 - 1)) * stride;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int j = k < 4 ? k : k + 1;
+                const int dy = j / 3 - 1, dx = j % 3 - 1;
+                const int yy = y + dy, xx = x + dx;
+                int off = INT_MIN;
+                if (yy >= 0 && yy < p.H && xx >= 0 && xx < W) {
+                    const int dq = dy * W + dx;
+                    if (p.ring_nb) {
+                        int r = hit.rp + dq;
+                        if (r < 0) r += ring_px;
+                        if (r >= ring_px) r -= ring_px;
+                        off = r * stride;
+                    } else {
+                        off = dq * stride;
+                    }
+                }
+                nb[k] = off;
+            }
         }
     }
-    float hA[KE], hB[KE], hC[KE], hD[KE], va[KE], vb[KE];
+    while (uni) {
+        const int ch = __ffsll((long long)uni) - 1;
+        uni &= uni - 1;
+        bool peak = false;
+        float v = 0.f;
+        if ((hit.mask >> ch) & 1ull) {
+            v = ring[hit.rp * stride + ch];
+            if (v >= thr_f) {   // the threshold may have risen since the scan; it is > 0, so score-0 entries never get here
+                float m = v;
+                if (p.ring_nb) {
 #pragma unroll
-    for (int k = 0; k < KE; ++k) hA[k] = hB[k] = hC[k] = hD[k] = va[k] = vb[k] = neg_inf();
-
-    uint32_t phase_bits = 0;
-    float thr_f = __uint_as_float(1u);  // smallest positive float: "score > 0" and "score >= threshold" in one compare
-    int trigger = 0;                    // this thread received a buffer position at/after the compaction mark
-
-    // rows ra-1 .. rb, two per barrier.  Four h register sets rotate with period 4 (= ring depth, so the slot is a
-    // compile-time constant), the two value sets with period 2: no register moves between rows.
-    // Row -1 of a top stripe is virtual: its register sets already hold -inf, so it is skipped.  Row H below a bottom
-    // stripe is a ring slot filled with -inf (fill_virtual_row): the loop treats it like any other row.
-#define CVM_ROW(J, HP, HC, HN, VC, VN) \
-    row_compute<J, KE, SLOTF, BULK>(c, r + J, pv, pl, pr, HP, HC, HN, VC, VN, phase_bits, thr_f, trigger)
-    for (int r = c.ra - 1; r <= c.rb; r += 4) {
-        if (r >= 0) CVM_ROW(0, hC, hD, hA, vb, va);
-        if (r + 1 <= c.rb) CVM_ROW(1, hD, hA, hB, va, vb);
-        step_end<SLOTF, BULK>(c, r, tid, thr_f, trigger);
-        if (r + 2 > c.rb) break;
-        CVM_ROW(2, hA, hB, hC, vb, va);
-        if (r + 3 <= c.rb) CVM_ROW(3, hB, hC, hD, va, vb);
-        step_end<SLOTF, BULK>(c, r + 2, tid, thr_f, trigger);
+                    for (int k = 0; k < 8; ++k)
+                        if (nb[k] != INT_MIN) m = fmaxf(m, ring[nb[k] + ch]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (nb[k] != INT_MIN) m = fmaxf(m, g_px[nb[k] + ch]);
+                }
+                peak = m == v;   // the value equals its 3x3 maximum (plateaus are all kept)
+            }
+        }
+        const unsigned pm = __ballot_sync(0xffffffffu, peak);
+        if (pm) {
+            const int leader = __ffs(pm) - 1;
+            unsigned base = 0;
+            if (lane == leader) base = (unsigned)atomicAdd(&h->count, __popc(pm));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (peak) {
+                const unsigned pos = base + __popc(pm & ((1u << lane) - 1u));
+                const unsigned bits = __float_as_uint(v);
+                const unsigned flat = (unsigned)hit.q * (unsigned)p.hm + (unsigned)ch;
+                cand[pos] = ((unsigned long long)bits << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
+                if (pos >= (unsigned)p.compact_at) *(volatile int*)&h->compact_flag = 1;
+                const unsigned bin = bits >> kScoreShift;
+                atomicAdd(&shist[bin], 1u);
+                if ((int)bin > *(volatile int*)&h->maxbin) atomicMax(&h->maxbin, (int)bin);
+            }
+        }
     }
-#undef CVM_ROW
+}
 
-    int n = s_count;
-    if (n > p.K) {
-        select_topk(c.cand, n, p.K, hist, c.keep, s_misc, &s_thr);
-        n = p.K;
+// bits of the heatmap channels of one pixel whose score reaches the threshold (called for the few pixels whose maximum does)
+template <int HM>
+__device__ __forceinline__ unsigned long long channel_mask(const float* px, int hm, float thr_f) {
+    unsigned long long m = 0ull;
+    if (HM > 0) {
+        unsigned lo = 0u;   // HM <= 32 in every instantiation
+#pragma unroll
+        for (int c = 0; c < HM; ++c) lo |= (px[c] >= thr_f ? 1u : 0u) << c;
+        m = lo;
+    } else {
+        for (int c = 0; c < hm; ++c)
+            if (px[c] >= thr_f) m |= 1ull << c;
     }
-    unsigned long long* out = p.keys + (size_t)blockIdx.x * p.K;
-    for (int i = tid; i < n; i += kThreads) out[i] = c.cand[i];
-    if (tid == 0) p.counts[blockIdx.x] = n;
+    return m;
+}
+
+// maximum over the HM leading floats of one pixel; STRIDE > 0: compile-time layout, widest aligned vector loads
+template <int STRIDE, int HM>
+__device__ __forceinline__ float pixel_max(const float* px, int hm) {
+    float m = __int_as_float(0xff800000);
+    if (STRIDE == 0) {
+        for (int c = 0; c < hm; ++c) m = fmaxf(m, px[c]);
+    } else if (STRIDE % 4 == 0) {
+#pragma unroll
+        for (int c = 0; c < HM; c += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(px + c);
+            m = fmaxf(m, t.x);
+            if (c + 1 < HM) m = fmaxf(m, t.y);
+            if (c + 2 < HM) m = fmaxf(m, t.z);
+            if (c + 3 < HM) m = fmaxf(m, t.w);
+        }
+    } else if (STRIDE % 2 == 0) {
+#pragma unroll
+        for (int c = 0; c < HM; c += 2) {
+            const float2 t = *reinterpret_cast<const float2*>(px + c);
+            m = fmaxf(m, t.x);
+            if (c + 1 < HM) m = fmaxf(m, t.y);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < HM; ++c) m = fmaxf(m, px[c]);
+    }
+    return m;
+}
+
+// Gathering of the scanner warps (called warp-uniformly at a step boundary).  A warp comes here when it saw the
+// compaction flag, or (at_segment_end) when it has finished the segment and wants the flush; whoever arrives waits for
+// all of them, then everybody takes the same decisions from state that cannot change while all are paused.
+__device__ __noinline__ void gather(const DecodeParams& p, bool at_segment_end, int seg) {
+    SharedHead* h = sm_head();
+    for (;;) {
+        DBG_STATE(at_segment_end ? 21 : 20);
+        group_sync(kScanThreads);   // everybody paused: no appends in flight
+        DBG_STATE(22);
+        const int flag = *(volatile int*)&h->compact_flag;
+        const int done = *(volatile int*)&h->seg_done;
+        group_sync(kScanThreads);
+        if (done == kScanWarps) {   // all warps finished the segment: publish it (selects when more than K are buffered)
+            flush_segment(p, seg);
+            return;
+        }
+        DBG_STATE(23);
+        if (flag) compact_buffer(p);        // clears the flag
+        DBG_STATE(24);
+        if (!at_segment_end) return;        // back to scanning; a warp waiting for the flush keeps gathering
+    }
+}
+
+
+__device__ __forceinline__ uint2 load_ctrl(const SharedHead* h) {
+    uint2 v;
+    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_u32(&h->thr_bits)) : "memory");
+    return v;
+}
+
+// Per-thread (warp-uniform) pipeline state of a scanner warp; lives in registers.
+struct ScanState {
+    float thr_f;          // threshold score this warp currently compares with
+    int waited, w_slot;   // granules [0, waited) have arrived; slot of granule `waited`
+    uint32_t w_parity;    // parity of the full-barrier phase of granule `waited`
+    int released, r_slot; // granules [0, released) were handed back by this warp
+};
+
+// Wait until granules [0, upto) have arrived.
+__device__ __forceinline__ void wait_until(const DecodeParams& p, ScanState& z, int upto) {
+    SharedHead* const h = sm_head();
+    while (z.waited < upto) {
+        // A warp blocked on data is at a safe point (it is not appending): it must join a compaction gather, or the
+        // warps behind it (whose releases the loader needs) would wait for it forever.  The votes keep the warp
+        // converged: the barrier can complete, and the flag can change, between two lanes' polls.
+        while (!__all_sync(0xffffffffu, mbar_try_wait(&h->full_bar[z.w_slot], z.w_parity))) {
+            if (__any_sync(0xffffffffu, load_ctrl(h).y != 0)) {
+                gather(p, false, 0);
+                z.thr_f = __uint_as_float(load_ctrl(h).x);
+            }
+        }
+        ++z.waited;
+        if (++z.w_slot == p.S) {
+            z.w_slot = 0;
+            z.w_parity ^= 1u;
+        }
+    }
+}
+
+// Hand granules [released, upto) back to the loader (one arrive per warp and granule).
+__device__ __forceinline__ void release_until(const DecodeParams& p, ScanState& z, int upto) {
+    if (z.released < upto) {
+        SharedHead* const h = sm_head();
+        __syncwarp();   // every lane is done reading them
+        while (z.released < upto) {
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&h->empty_bar[z.r_slot]);
+            ++z.released;
+            if (++z.r_slot == p.S) z.r_slot = 0;
+        }
+    }
+}
+
+// STRIDE/HM = 0: runtime pixel stride / heatmap channel count.  BULK: granules arrive by bulk async copy (needs 16-byte
+// aligned granules); otherwise the loader warp copies them with plain loads.
+template <int STRIDE, int HM, bool BULK>
+__global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_constant__ DecodeParams p) {
+    SharedHead* const h = sm_head();
+    float* const ring = sm_ring();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = p.S, T = p.T, spi = p.spi, HW = p.HW, hg = p.halo_g;
+    const int stride = STRIDE ? STRIDE : p.stride;
+
+    // this CTA's contiguous range of the flat step list; granule `seq` of the CTA is flat step s0 - lead + seq
+    const long long G = gridDim.x, g = blockIdx.x;
+    const long long s0 = g * p.n_steps / G, s1 = (g + 1) * p.n_steps / G;
+    if (s0 >= s1) return;
+    const long long img0 = s0 / spi, imgL = (s1 - 1) / spi;
+    const int st0 = (int)(s0 - img0 * spi), stL = (int)((s1 - 1) - imgL * spi);
+    const int n_local = (int)(s1 - s0);
+    const int lead = min(hg, st0);              // history granules before the first step (same image only)
+    const int tail = min(hg, spi - 1 - stL);    // lookahead granules after the last step (same image only)
+    const int n_load = lead + n_local + tail;
+
+    if (tid == 0) {
+        for (int k = 0; k < S; ++k) {
+            mbar_init(&h->full_bar[k], 1);
+            mbar_init(&h->empty_bar[k], kScanWarps);
+        }
+        mbar_fence_init();
+        h->count = 0;
+        h->thr = 0ull;
+        h->thr_bits = p.thr0_bits;   // smallest positive float: "score > 0" and "score >= threshold" in one compare
+        h->scanned = 0;
+        h->maxbin = 0;
+        h->compact_flag = 0;
+        h->seg_done = 0;
+    }
+    for (int k = tid; k < kScoreBins; k += kThreads) sm_shist(p)[k] = 0u;
+    __syncthreads();   // the only CTA-wide barrier: from here on the loader warp and the scanner warps run on their own
+
+    if (warp == kScanWarps) {
+        // ---- loader warp: granule `seq` goes to slot seq % S once all scanner warps have released its previous tenant ----
+        int slot = 0, gi = st0 - lead;
+        long long l_img = img0;
+        uint32_t e_parity = 0;   // parity of the empty-barrier phase that frees a slot for its next tenant
+        for (int seq = 0; seq < n_load; ++seq) {
+#ifdef CVM_WATCHDOG
+            if (seq >= S) {
+                long long spins = 0;
+                while (!mbar_try_wait(&h->empty_bar[slot], e_parity)) {
+                    if (++spins > 16000000LL) {
+                        if (lane == 0)
+                        {
+                            printf("loader stuck: cta %d seq %d n_load %d slot %d flag %d seg_done %d count %d\n", (int)blockIdx.x, seq,
+                                   n_load, slot, h->compact_flag, h->seg_done, h->count);
+                            volatile int* d = h->dbg_state;
+                            printf("  states cta %d: %d %d %d %d %d %d %d %d %d %d %d %d %d %d %d %d\n", (int)blockIdx.x, d[0], d[1], d[2], d[3],
+                                   d[4], d[5], d[6], d[7], d[8], d[9], d[10], d[11], d[12], d[13], d[14], d[15]);
+                        }
+                        __trap();
+                    }
+                }
+            }
+#else
+            if (seq >= S) mbar_wait(&h->empty_bar[slot], e_parity);
+#endif
+            const int npx = min(T, HW - gi * T);
+            const float* src = p.yp + ((size_t)l_img * HW + (size_t)gi * T) * stride;
+            float* dst = ring + (size_t)slot * p.gran_floats;
+            if (BULK) {
+                if (lane == 0) {
+                    const uint32_t bytes = (uint32_t)npx * (uint32_t)stride * 4u;
+                    mbar_arrive_expect_tx(&h->full_bar[slot], bytes);
+                    bulk_g2s(dst, src, bytes, &h->full_bar[slot]);
+                }
+            } else {
+                const int nf = npx * stride;
+                for (int k = lane; k < nf; k += 32) dst[k] = src[k];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&h->full_bar[slot]);   // release: the stores above are visible to the waiters
+            }
+            if (++slot == S) {
+                slot = 0;
+                if (seq >= S) e_parity ^= 1u;
+            }
+            if (++gi == spi) {
+                gi = 0;
+                ++l_img;
+            }
+        }
+        return;
+    }
+
+    // ---- scanner warps ----
+    ScanState z;
+    z.thr_f = __uint_as_float(p.thr0_bits);
+    z.waited = z.w_slot = z.released = z.r_slot = 0;
+    z.w_parity = 0u;
+
+    long long img = img0;
+    int st = st0;
+    int cur_slot = lead;     // slot of the current step's granule (lead <= halo_g < S)
+    Hit prev;                // this lane's pixel of the previous step, if it reached the threshold: waits for its 3x3 test
+    prev.mask = 0ull;
+    prev.q = prev.rp = 0;
+
+    for (int i = 0; i < n_local; ++i) {
+        const int seq = i + lead;
+        const int q0 = st * T, npx = min(T, HW - q0);
+        // last granule of this image that this CTA fetches
+        const int seq_last = min(seq + (spi - 1 - st), n_load - 1);
+        // this step's granule, and the lookahead of the previous step's pixels (W + 1 pixels past its end)
+        DBG_STATE(100 + i * 1000);
+        wait_until(p, z, min(max(seq, seq - 1 + hg), seq_last) + 1);
+        DBG_STATE(101 + i * 1000);
+        test_hits(p, img, prev, z.thr_f);
+        // this step: one compare per pixel
+        DBG_STATE(102 + i * 1000);
+        const int rp = cur_slot * T + tid;   // ring position of this lane's pixel
+        Hit cur;
+        cur.mask = 0ull;
+        cur.q = q0 + tid;
+        cur.rp = rp;
+        if (tid < npx) {
+            const float* px = ring + (size_t)rp * stride;
+            if (pixel_max<STRIDE, HM>(px, p.hm) >= z.thr_f) cur.mask = channel_mask<HM>(px, p.hm, z.thr_f);
+        }
+        // the next step tests this step's pixels and needs halo_g granules of history before it: the rest is dead
+        release_until(p, z, seq - hg);
+        __syncwarp();   // converged: the control word below is one broadcast load, the same pair for all lanes
+        const uint2 ctrl = load_ctrl(h);
+        z.thr_f = __uint_as_float(ctrl.x);   // stale values are still valid bounds
+        const bool segment_end = (st + 1 == spi) || (i + 1 == n_local);
+        DBG_STATE(103 + i * 1000);
+        if (!segment_end) {
+            if (warp == 1) scan_threshold(h, sm_shist(p), p.K, lane);
+            if (__any_sync(0xffffffffu, ctrl.y != 0)) {   // a vote: the decision to gather must be warp-uniform
+                gather(p, false, 0);
+                z.thr_f = __uint_as_float(load_ctrl(h).x);
+            }
+            prev = cur;
+            ++st;
+        } else {
+            // drain: test this step's hits now (the lookahead, if any, belongs to the next CTA's range and was fetched too)
+            wait_until(p, z, min(seq + hg, seq_last) + 1);
+            test_hits(p, img, cur, z.thr_f);
+            const bool image_end = st + 1 == spi;
+            release_until(p, z, image_end ? seq + 1 : n_load);   // the rest of the image / of the range is dead
+            if (lane == 0) atomicAdd(&h->seg_done, 1);
+            gather(p, true, (int)(img - img0));
+            z.thr_f = __uint_as_float(p.thr0_bits);
+            prev.mask = 0ull;
+            if (image_end) {
+                st = 0;
+                ++img;
+            }
+        }
+        if (++cur_slot == S) cur_slot = 0;
+    }
 }
 
 struct MergeParams {
     const float* yp;
-    int stride, H, W, hm, K, nbx, n_big, m_small;
+    int stride, H, W, hm, K;
+    int spi, grid, max_segs, seg_keys;
+    long long n_steps;
     int off_roff, off_box, off_track;
     float R;
     const cvm_roi* rois;
@@ -446,50 +707,57 @@ struct MergeParams {
     float* track;
 };
 
-__global__ void __launch_bounds__(kThreads) decode_merge_kernel(const MergeParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+__global__ void __launch_bounds__(kMergeThreads) decode_merge_kernel(const MergeParams p) {
     __shared__ unsigned int hist[256];
     __shared__ int s_misc[4];
     __shared__ unsigned long long s_thr;
 
     const int tid = threadIdx.x, b = blockIdx.x, K = p.K;
-    const int max_tiles = p.nbx * p.m_small;
-    unsigned long long* const all = reinterpret_cast<unsigned long long*>(smem_raw);   // [max_tiles*K]
-    unsigned long long* const keep = all + (size_t)max_tiles * K;                      // [K]
+    unsigned long long* const all = reinterpret_cast<unsigned long long*>(g_smem);   // [kMergeCap + K]
+    unsigned long long* const keep = all + kMergeCap + K;                              // [K]
     unsigned long long* const sorted = keep + K;                                       // [K]
 
-    // gather the keys of this image's tiles (a handful of tiles; walked by every thread, copied cooperatively)
+    // the scan CTAs whose step range [g*n/G, (g+1)*n/G) overlaps this image's steps [lo, hi)
+    const long long n_ch = p.n_steps, G = p.grid;
+    const long long lo = (long long)b * p.spi, hi = lo + p.spi;
+    long long g = lo * G / n_ch;
+    while (g + 1 < G && (g + 1) * n_ch / G <= lo) ++g;
     int n = 0;
-    for (int bx = 0; bx < p.nbx; ++bx) {
-        const int col = b * p.nbx + bx;
-        const int t0 = col < p.n_big ? col : p.n_big + (col - p.n_big) * p.m_small;
-        const int nt = col < p.n_big ? 1 : p.m_small;
-        for (int t = t0; t < t0 + nt; ++t) {
-            const int cnt = p.counts[t];
-            const unsigned long long* src = p.keys + (size_t)t * K;
-            for (int i = tid; i < cnt; i += kThreads) all[n + i] = src[i];
-            n += cnt;
+    for (; g < G; ++g) {
+        const long long s0 = g * n_ch / G, s1 = (g + 1) * n_ch / G;
+        if (s0 >= hi) break;
+        if (s1 <= s0) continue;
+        const int seg = (int)(b - s0 / p.spi);
+        const size_t o = (size_t)g * p.max_segs + seg;
+        const int cnt = p.counts[o];
+        if (n + cnt > kMergeCap) {   // cnt <= seg_keys <= kMergeCap / 4, so n > K here
+            group_sync(kMergeThreads);
+            select_topk(all, n, K, hist, keep, s_misc, &s_thr, kMergeThreads);
+            n = K;
         }
+        const unsigned long long* src = p.keys + o * p.seg_keys;
+        for (int i = tid; i < cnt; i += kMergeThreads) all[n + i] = src[i];
+        n += cnt;
     }
-    __syncthreads();
+    group_sync(kMergeThreads);
     if (n > K) {
-        select_topk(all, n, K, hist, keep, s_misc, &s_thr);
+        select_topk(all, n, K, hist, keep, s_misc, &s_thr, kMergeThreads);
         n = K;
     }
     // rank sort (keys are distinct): descending
-    for (int i = tid; i < n; i += kThreads) {
+    for (int i = tid; i < n; i += kMergeThreads) {
         const unsigned long long k = all[i];
         int rank = 0;
         for (int j = 0; j < n; ++j) rank += all[j] > k;
         sorted[rank] = k;
     }
-    __syncthreads();
+    group_sync(kMergeThreads);
 
     const int hm = p.hm, W = p.W;
     const long long n_total = (long long)p.H * W * hm;
     const int K_eff = (long long)K < n_total ? K : (int)n_total;
     const cvm_roi roi = p.rois ? p.rois[b] : cvm_roi{1.0f, 0.0f, 0.0f, 0.0f};
-    for (int i = tid; i < K; i += kThreads) {
+    for (int i = tid; i < K; i += kMergeThreads) {
         const size_t o = (size_t)b * K + i;
         float score = 0.f;
         long long fl = -1;
@@ -551,71 +819,68 @@ __global__ void __launch_bounds__(kThreads) decode_merge_kernel(const MergeParam
     }
 }
 
-struct Tiling {
-    int variant;   // 0: <5, 2112>, 1: <8, 3328>
-    int KE, slot_floats;
-    int TW, nbx, n_big, m_small, SR_small, n_tiles, cap, compact_at;
-    size_t smem_stream, smem_merge, ws_keys, ws_total;
+
+struct Plan {
+    int T, spi, S, ring_nb, halo_g, gran_floats, cap, compact_at, grid, max_segs, seg_keys;
+    long long n_steps;
+    size_t smem_scan, smem_merge, ws_keys, ws_total;
 };
 
-int plan_tiling(const cvm_layout* L, int stride, int B, int K, Tiling* t) {
-    const int hm = L->hm, H = L->H, W = L->W;
-    // variant 0 unless its ring slot cannot hold a useful band at this pixel stride
-    t->variant = ((2112 - 12) / stride - 2 >= 16) ? 0 : 1;
-    t->KE = t->variant == 0 ? 5 : 8;
-    t->slot_floats = t->variant == 0 ? 2112 : 3328;
-    int tw_max = (kThreads * t->KE) / hm;
-    // a row segment (band + 1-pixel halo each side + alignment slack + sentinels) must fit the fixed ring slot
-    const int tw_slot = (t->slot_floats - 12) / stride - 2;
-    if (tw_max > tw_slot) tw_max = tw_slot;
-    if (tw_max < 1) return CVM_ERR_ARG;
-    t->nbx = (W + tw_max - 1) / tw_max;
-    t->TW = (W + t->nbx - 1) / t->nbx;
-    t->compact_at = K + kSlack;
-    t->cap = t->compact_at + 2 * t->TW * hm;   // two rows of appends between barriers
-    t->smem_stream = (size_t)kSlots * t->slot_floats * 4 + (size_t)t->cap * 8 + (size_t)K * 8 + (size_t)kScoreBins * 4;
-    // Per-CTA fixed costs (threshold bootstrap, selects) favour tall tiles, whole waves favour many small ones: columns
-    // (image x band) are processed top to bottom by one CTA each for as many whole waves as there are, the rest is cut
-    // into m stripes (longest tiles first, short tiles fill the tail).
-    int per_sm = (int)((220 * 1024) / (t->smem_stream + 2048));
-    const int reg_cap = t->variant == 0 ? 3 : 1;   // CTAs/SM allowed by the register budget of each instantiation
-    if (per_sm > reg_cap) per_sm = reg_cap;
-    if (per_sm < 1) per_sm = 1;
-    const long long slots = (long long)cvm_num_sms() * per_sm;
-    const long long C = (long long)B * t->nbx;
-    long long n_big = (C / slots) * slots;
-    long long rem = C - n_big;
-    int max_m = (H + 7) / 8;   // at least 8 rows per stripe (halo overhead <= 25%)
-    if (max_m > 8) max_m = 8;
-    while (max_m > 1 && (long long)max_m * t->nbx * K > 16384) --max_m;   // merge kernel: <= 16K keys per image
-    int best_m = 1;
-    double best_cost = 1e30;
-    for (int m = 1; m <= max_m; ++m) {
-        const long long waves = (rem * m + slots - 1) / slots;
-        const double cost = (double)waves * (1.0 / m + 0.04);
-        if (cost < best_cost - 1e-12) {
-            best_cost = cost;
-            best_m = m;
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+int plan_decode(const cvm_layout* L, int stride, int B, int K, Plan* t) {
+    const int hm = L->hm, W = L->W;
+    const long long HW = (long long)L->H * W;
+    // step = ring granule: one pixel per scanner thread, fewer when that could append more than kMaxAppend candidates
+    // before every warp has reached a safe point, or when the image is smaller
+    int T = kScanThreads;
+    if ((long long)T * hm > kMaxAppend) T = (kMaxAppend / hm) / 32 * 32;
+    if (HW < T) T = (int)((HW + 31) / 32 * 32);
+    for (;; T -= 32) {
+        if (T < 32) return CVM_ERR_ARG;
+        t->compact_at = K + kSlack;
+        t->cap = t->compact_at + 1 + T * hm;
+        const size_t fixed = smem_bytes(0, 0, t->cap, K);
+        const size_t gran_bytes = (size_t)T * stride * 4;
+        if (fixed + 4 * gran_bytes > (size_t)kSmemBudget) continue;
+        int S = (int)(((size_t)kSmemBudget - fixed) / gran_bytes);
+        if (S > kMaxSlots) S = kMaxSlots;
+        // ring mode keeps 2 * halo_g + 1 granules resident (history and lookahead of the tested step), global-neighbour
+        // mode keeps 2; both want at least two more in flight
+        const int hg = (W + 1 + T - 1) / T;
+        if (S >= 2 * hg + 3) {
+            t->ring_nb = 1;
+            t->halo_g = hg;
+            t->S = S < 2 * hg + 5 ? S : 2 * hg + 5;
+        } else {
+            t->ring_nb = 0;
+            t->halo_g = 0;
+            t->S = S < 6 ? S : 6;
         }
+        t->gran_floats = T * stride;
+        break;
     }
-    if (const char* e = getenv("CVM_DECODE_NSY")) {  // experiment knob: uniform stripes
-        const int v = atoi(e);
-        if (v >= 1 && v <= (H + 7) / 8 && (long long)v * t->nbx * K <= 16384) {
-            n_big = 0;
-            rem = C;
-            best_m = v;
-        }
+    {
+        const int v = env_int("CVM_DECODE_S", 0);   // experiment knob: ring depth
+        if (v >= 2 * t->halo_g + 3 && v <= kMaxSlots && smem_bytes(v, t->gran_floats, t->cap, K) <= (size_t)kSmemBudget) t->S = v;
     }
-    if ((long long)best_m * t->nbx * K > 16384) return CVM_ERR_ARG;
-    t->n_big = (int)n_big;
-    t->m_small = best_m;
-    t->SR_small = (H + best_m - 1) / best_m;
-    const long long n_tiles = n_big + rem * best_m;
-    if (n_tiles >= 2147483647LL) return CVM_ERR_ARG;
-    t->n_tiles = (int)n_tiles;
-    t->smem_merge = ((size_t)t->nbx * best_m * K + 2 * (size_t)K) * 8;
-    t->ws_keys = (size_t)n_tiles * K * 8;
-    t->ws_total = t->ws_keys + (size_t)n_tiles * 4;
+    t->T = T;
+    t->spi = (int)((HW + T - 1) / T);
+    t->n_steps = (long long)B * t->spi;
+    long long grid = cvm_num_sms();
+    if (grid > t->n_steps) grid = t->n_steps;
+    if (grid < 1) grid = 1;
+    t->grid = (int)grid;
+    const long long len = (t->n_steps + grid - 1) / grid;
+    t->max_segs = (int)((len - 1) / t->spi + 2);
+    t->smem_scan = smem_bytes(t->S, t->gran_floats, t->cap, K);
+    t->smem_merge = ((size_t)kMergeCap + 3 * (size_t)K) * 8;
+    t->seg_keys = K > kSegKeys ? K : kSegKeys;
+    t->ws_keys = (size_t)grid * t->max_segs * t->seg_keys * 8;
+    t->ws_total = t->ws_keys + (size_t)grid * t->max_segs * 4;
     return CVM_OK;
 }
 
@@ -629,12 +894,27 @@ int check_decode_args(const cvm_layout* L, int stride, int B, int K) {
     return CVM_OK;
 }
 
+template <int STRIDE, int HM>
+int launch_scan(const DecodeParams& p, const Plan& t, bool bulk, cudaStream_t st) {
+    if (bulk) {
+        CVM_CHECK_CUDA(cudaFuncSetAttribute(decode_scan_kernel<STRIDE, HM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)t.smem_scan));
+        decode_scan_kernel<STRIDE, HM, true><<<t.grid, kThreads, t.smem_scan, st>>>(p);
+    } else {
+        CVM_CHECK_CUDA(cudaFuncSetAttribute(decode_scan_kernel<STRIDE, HM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)t.smem_scan));
+        decode_scan_kernel<STRIDE, HM, false><<<t.grid, kThreads, t.smem_scan, st>>>(p);
+    }
+    CVM_CHECK_LAUNCH("decode_scan_kernel");
+    return CVM_OK;
+}
+
 }  // namespace
 
 extern "C" size_t cvm_decode_topk_workspace_bytes(const cvm_layout* L, int pred_stride, int B, int K) {
     if (check_decode_args(L, pred_stride, B, K) != CVM_OK) return 0;
-    Tiling t;
-    if (plan_tiling(L, pred_stride, B, K, &t) != CVM_OK) return 0;
+    Plan t;
+    if (plan_decode(L, pred_stride, B > 0 ? B : 1, K, &t) != CVM_OK) return 0;
     return t.ws_total;
 }
 
@@ -645,56 +925,51 @@ extern "C" int cvm_decode_topk(const cvm_layout* L, const float* y_pred, int pre
     if (rc != CVM_OK) return rc;
     CVM_CHECK_ARG(y_pred && scores && cls && flat && centers && boxes && ws, "NULL pointer argument");
     if (B == 0) return CVM_OK;
-    Tiling t;
-    rc = plan_tiling(L, pred_stride, B, K, &t);
-    CVM_CHECK_ARG(rc == CVM_OK, "no tiling for H=%d W=%d hm=%d K=%d", L->H, L->W, L->hm, K);
+    Plan t;
+    rc = plan_decode(L, pred_stride, B, K, &t);
+    CVM_CHECK_ARG(rc == CVM_OK, "no tiling for H=%d W=%d hm=%d stride=%d K=%d", L->H, L->W, L->hm, pred_stride, K);
     if (ws_bytes < t.ws_total) {
         cvm_set_error("workspace too small: %zu < %zu", ws_bytes, t.ws_total);
         return CVM_ERR_WS;
     }
-    CVM_CHECK_ARG(t.smem_stream <= 200 * 1024 && t.smem_merge <= 200 * 1024, "shared memory budget exceeded");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     DecodeParams p;
     memset(&p, 0, sizeof(p));
     p.yp = y_pred;
-    p.total_floats = (long long)B * L->H * L->W * pred_stride;
     p.stride = pred_stride;
     p.H = L->H;
     p.W = L->W;
     p.hm = L->hm;
     p.K = K;
-    p.TW = t.TW;
-    p.nbx = t.nbx;
-    p.n_big = t.n_big;
-    p.m_small = t.m_small;
-    p.SR_small = t.SR_small;
-    p.slot_floats = t.slot_floats;
+    p.HW = L->H * L->W;
+    p.T = t.T;
+    p.spi = t.spi;
+    p.n_steps = t.n_steps;
+    p.S = t.S;
+    p.ring_nb = t.ring_nb;
+    p.halo_g = t.halo_g;
+    p.gran_floats = t.gran_floats;
     p.cap = t.cap;
     p.compact_at = t.compact_at;
-    p.use_bulk = cvm_aligned16(y_pred);
-    p.inv_hm = 1.0f / (float)L->hm;
+    p.max_segs = t.max_segs;
+    p.seg_keys = t.seg_keys;
     p.keys = static_cast<unsigned long long*>(ws);
     p.counts = reinterpret_cast<int*>(static_cast<unsigned char*>(ws) + t.ws_keys);
-
-    const long long grid = t.n_tiles;
-    // the bulk-copy engine needs 16-byte granules: base pointer aligned, every row starting at the same offset mod 4
-    // floats (W*stride % 4 == 0) and the rounded-up end of the last row inside the tensor (total % 4 == 0)
-    const bool bulk = cvm_aligned16(y_pred) && (((long long)L->W * pred_stride) % 4 == 0) && (p.total_floats % 4 == 0);
-#define CVM_LAUNCH_STREAM(KE_, SLOTF_, MIN_, BULK_)                                                                           \
-    do {                                                                                                                      \
-        CVM_CHECK_CUDA(cudaFuncSetAttribute(decode_stream_kernel<KE_, SLOTF_, MIN_, BULK_>,                                   \
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_stream));                \
-        decode_stream_kernel<KE_, SLOTF_, MIN_, BULK_><<<(unsigned)grid, kThreads, t.smem_stream, st>>>(p);                   \
-    } while (0)
-    if (t.variant == 0) {
-        if (bulk) CVM_LAUNCH_STREAM(5, 2112, 3, true);
-        else CVM_LAUNCH_STREAM(5, 2112, 3, false);
-    } else {
-        if (bulk) CVM_LAUNCH_STREAM(8, 3328, 1, true);
-        else CVM_LAUNCH_STREAM(8, 3328, 1, false);
+    p.thr0_bits = 1u;
+    p.inv_W = 1.0f / (float)L->W;
+    if (const char* e = getenv("CVM_DECODE_THR0")) {   // experiment knob (results are wrong when set): start threshold
+        const float f = (float)atof(e);
+        memcpy(&p.thr0_bits, &f, 4);
     }
-#undef CVM_LAUNCH_STREAM
-    CVM_CHECK_LAUNCH("decode_stream_kernel");
+
+    // the bulk-copy engine needs 16-byte granules: base pointer aligned and every image a whole number of them (full
+    // granules are Pg*stride*4 bytes with Pg % 32 == 0, the partial last granule of an image then ends on one too)
+    const bool bulk = cvm_aligned16(y_pred) && (((long long)p.HW * pred_stride) % 4 == 0);
+    if (pred_stride == 14 && L->hm == 10) rc = launch_scan<14, 10>(p, t, bulk, st);        // CenterNet, 10 classes
+    else if (pred_stride == 16 && L->hm == 10) rc = launch_scan<16, 10>(p, t, bulk, st);   // CenterTracker
+    else if (pred_stride == 20 && L->hm == 10) rc = launch_scan<20, 10>(p, t, bulk, st);   // multitask head
+    else rc = launch_scan<0, 0>(p, t, bulk, st);
+    if (rc != CVM_OK) return rc;
 
     MergeParams m;
     memset(&m, 0, sizeof(m));
@@ -704,9 +979,11 @@ extern "C" int cvm_decode_topk(const cvm_layout* L, const float* y_pred, int pre
     m.W = L->W;
     m.hm = L->hm;
     m.K = K;
-    m.nbx = t.nbx;
-    m.n_big = t.n_big;
-    m.m_small = t.m_small;
+    m.spi = t.spi;
+    m.grid = t.grid;
+    m.max_segs = t.max_segs;
+    m.seg_keys = t.seg_keys;
+    m.n_steps = t.n_steps;
     m.off_roff = L->off_roff;
     m.off_box = L->off_box;
     m.off_track = track ? L->off_track : -1;
@@ -721,7 +998,7 @@ extern "C" int cvm_decode_topk(const cvm_layout* L, const float* y_pred, int pre
     m.boxes = boxes;
     m.track = track;
     CVM_CHECK_CUDA(cudaFuncSetAttribute(decode_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem_merge));
-    decode_merge_kernel<<<B, kThreads, t.smem_merge, st>>>(m);
+    decode_merge_kernel<<<B, kMergeThreads, t.smem_merge, st>>>(m);
     CVM_CHECK_LAUNCH("decode_merge_kernel");
     return CVM_OK;
 }

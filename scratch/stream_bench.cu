@@ -1,0 +1,129 @@
+// Microbenchmark: how fast can persistent CTAs stream HBM through a shared-memory ring fed by 1-D bulk async copies?
+// usage: stream_bench <total_MB> <granule_bytes> <slots> <ctas_per_sm> <threads> <mode>
+// mode 0: consumers only wait+release; 1: consumers also read the granule (LDS.64 per 56 B pixel, max)
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../computer-vision-models_b200/csrc/common.cuh"
+
+void cvm_set_error(const char*, ...) {}
+int cvm_num_sms() { return 148; }
+
+__global__ void __launch_bounds__(1024, 1) stream_kernel(const float* src, size_t total_bytes, int gran_bytes, int S, int mode,
+                                                         float* out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + 32;
+    float* ring = reinterpret_cast<float*>(smem + 1024);
+    const int tid = threadIdx.x, nthr = blockDim.x, ncons = nthr - 32, warp = tid >> 5, lane = tid & 31;
+    const size_t n_gran = total_bytes / gran_bytes;
+    const size_t g0 = blockIdx.x * n_gran / gridDim.x, g1 = (blockIdx.x + 1) * n_gran / gridDim.x;
+    const int n = (int)(g1 - g0);
+    if (tid == 0) {
+        for (int k = 0; k < S; ++k) {
+            mbar_init(&full[k], 1);
+            mbar_init(&empty[k], ncons / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == ncons / 32) {
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t par = 0;
+            for (int i = 0; i < n; ++i) {
+                if (i >= S) mbar_wait(&empty[slot], par);
+                mbar_arrive_expect_tx(&full[slot], gran_bytes);
+                bulk_g2s(reinterpret_cast<unsigned char*>(ring) + (size_t)slot * gran_bytes,
+                         reinterpret_cast<const unsigned char*>(src) + (g0 + i) * gran_bytes, gran_bytes, &full[slot]);
+                if (++slot == S) {
+                    slot = 0;
+                    if (i >= S) par ^= 1;
+                }
+            }
+        }
+        return;
+    }
+    int slot = 0;
+    uint32_t par = 0;
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) {
+        mbar_wait(&full[slot], par);
+        if (mode == 1) {
+            const float* g = ring + (size_t)slot * (gran_bytes / 4);
+            for (int px = tid; px * 56 + 56 <= gran_bytes; px += ncons) {
+                const float2* p2 = reinterpret_cast<const float2*>(g + px * 14);
+                float m = 0.f;
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    const float2 t = p2[c];
+                    m = fmaxf(m, fmaxf(t.x, t.y));
+                }
+                acc = fmaxf(acc, m);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[slot])) : "memory");
+        if (++slot == S) {
+            slot = 0;
+            par ^= 1;
+        }
+    }
+    if (acc == 12345.f) out[0] = acc;
+}
+
+// plain vectorised read for comparison
+__global__ void __launch_bounds__(512) ldg_kernel(const float4* src, size_t n4, float* out) {
+    float acc = 0.f;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        const float4 a = __ldcs(src + i), b = __ldcs(src + i + stride), c = __ldcs(src + i + 2 * stride), d = __ldcs(src + i + 3 * stride);
+        acc = fmaxf(acc, fmaxf(fmaxf(a.x, b.y), fmaxf(c.z, d.w)));
+    }
+    for (; i < n4; i += stride) acc = fmaxf(acc, __ldcs(src + i).x);
+    if (acc == 12345.f) out[0] = acc;
+}
+
+int main(int argc, char** argv) {
+    const size_t total = (size_t)atoi(argv[1]) << 20;
+    float *src, *out;
+    cudaMalloc(&src, 2 * total);
+    cudaMalloc(&out, 4);
+    cudaMemset(src, 0, 2 * total);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int a = 2; a + 4 < argc + 0 || a + 4 == argc - 0; a += 5) {
+        if (a + 4 >= argc) break;
+        const int gran = atoi(argv[a]), S = atoi(argv[a + 1]), cps = atoi(argv[a + 2]), thr = atoi(argv[a + 3]), mode = atoi(argv[a + 4]);
+        const size_t smem = 1024 + (size_t)gran * S;
+        cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const size_t use = total / gran * gran;
+        float best = 1e9;
+        for (int it = 0; it < 6; ++it) {
+            cudaEventRecord(e0);
+            stream_kernel<<<148 * cps, thr, smem>>>(src + (it & 1) * (total / 4), use, gran, S, mode, out);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (it >= 2 && ms < best) best = ms;
+        }
+        printf("gran %6d S %2d ctas/sm %d thr %4d mode %d smem %6zu: %.4f ms %.0f GB/s  (%s)\n", gran, S, cps, thr, mode, smem, best,
+               use / best / 1e6, cudaGetErrorString(cudaGetLastError()));
+    }
+    float best = 1e9;
+    for (int it = 0; it < 6; ++it) {
+        cudaEventRecord(e0);
+        ldg_kernel<<<148 * 4, 512>>>(reinterpret_cast<const float4*>(src + (it & 1) * (total / 4)), total / 16, out);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (it >= 2 && ms < best) best = ms;
+    }
+    printf("ldg float4 x4 unrolled, 592 CTAs x 512: %.4f ms %.0f GB/s\n", best, total / best / 1e6);
+    return 0;
+}

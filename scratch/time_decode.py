@@ -1,0 +1,33 @@
+import os, sys, time, subprocess
+sys.path.insert(0, "/root/repo/computer-vision-models_b200"); sys.path.insert(0, "/root/repo")
+import torch
+from cvmhot import ops
+from cvmhot.layout import layout_from_params
+from cvmhot.models.centernet import CenternetParams
+H, W, C, B = 128, 384, 10, 256
+p = CenternetParams(C, True); p.INPUT_HEIGHT, p.INPUT_WIDTH = H*2, W*2
+L = layout_from_params(p)
+dev = torch.device("cuda", 0)
+g = torch.Generator(device=dev).manual_seed(1)
+yp = torch.empty((B, H, W, L.Cp), device=dev)
+yp[..., :C] = torch.sigmoid(torch.randn((B, H, W, C), device=dev, generator=g) * 1.5 - 4.0)
+yp[..., C:] = torch.rand((B, H, W, L.Cp - C), device=dev, generator=g) * 40
+yp2 = yp.clone()
+def run(tag):
+    for _ in range(3): ops.decode_topk(L, yp, K=100)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 10
+    e0.record()
+    for i in range(n): ops.decode_topk(L, yp if i % 2 else yp2, K=100)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    print(f"{tag:40s} {ms:.4f} ms  {yp.numel()*4/ms/1e6:.0f} GB/s", flush=True)
+for env in sys.argv[1:]:
+    for kv in env.split(","):
+        if kv and kv != "-":
+            k, v = kv.split("="); os.environ[k] = v
+    run(env)
+    for kv in env.split(","):
+        if kv and kv != "-":
+            os.environ.pop(kv.split("=")[0])
