@@ -2,23 +2,33 @@
 //
 // Replaces fill_heatmap (reference models/centernet/processor.py:17-38, a numba double loop per object) and the render
 // part of ProcessImages.process (processor.py:264-334) for a whole batch; also gen_prev_heatmap
-// (models/centertracker/processor.py:22-41) with n_planes = 1 and no weights plane.
+// (models/centertracker/processor.py:22-41) with one plane and no weights plane.
 //
 // Bound: HBM writes.  Algorithmic bytes per image: 4*H*W*Ct, every byte written exactly once (zeros included).
 //
-// Structure: one CTA per tile of `rows` full image rows.  The (hm + 1) planes that can be non-trivial (heatmap
-// channels + weights) live in shared memory as SoA planes; each thread OWNS a set of columns, so the max/min-combine
-// over all objects of the image needs neither atomics nor barriers.  Gaussian argument and exp are evaluated in fp64
-// (the reference does fp64 scalar math and stores fp32; B200 has full-rate-enough fp64 for ~1 exp per covered pixel).
-// The tile is then composed to NHWC and streamed out with 128-bit stores; the handful of regression targets at centre
-// pixels are patched afterwards by the same CTA.
+// Structure: y_true is one flat list of chunks (P consecutive pixels of one image, all channels: a contiguous piece of
+// the NHWC tensor).  The list is cut into equal contiguous ranges, one persistent CTA per range (two per SM).  A chunk is
+// built in shared memory in its FINAL layout: a pattern fill (zeros, ones in the weights channel); then one warp per
+// (object, 32-column segment) work unit walks the unit's rows, lane = column, and max-/min-combines the gaussian into the
+// chunk with shared integer atomics on the float bit patterns (windows of different objects overlap); then ignore areas
+// and the handful of regression targets at centre pixels are written, and ONE bulk async copy (TMA engine: UBLKCP,
+// shared -> global) streams the chunk out while the CTA builds the next one in the other buffer.  No store instruction
+// touches global memory on the fast path.  All gaussian math is fp64 like the reference's (scalar fp64 stored as fp32);
+// the separable factors exp(-ax), exp(-ay) are tabulated (per image / per chunk), see render_kernel.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;   // power of two: column ownership is x & (kThreads - 1)
-constexpr int kMaxObjSmem = 96;  // objects are processed in chunks of this many
-constexpr int kMaxIgnSmem = 16;  // ignore boxes cached in shared memory per band (more are read from global)
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxObjSmem = 64;   // objects are processed in batches of this many
+constexpr int kMaxIgnSmem = 16;     // ignore boxes cached in shared memory per image (more are read from global)
+constexpr int kChunkBytes = 43008;   // staging buffer size: two buffers per CTA, two CTAs per SM
+constexpr int kMaxUnits = 512;       // (object, 32-column segment) work units per chunk and object batch
+constexpr int kColTab = 1024;        // entries of the per-image column-factor table (objects that do not fit use exp)
+constexpr int kRowTab = 1024;        // entries of the per-image row-factor table
 
 struct RenderParams {
     const cvm_obj* objs;
@@ -27,20 +37,22 @@ struct RenderParams {
     const int32_t* ign_offsets;
     float* out;        // [B,H,W,Cout]
     int H, W, Cout;
-    int n_planes;      // heatmap planes kept in smem (hm)
+    int HW;
+    int n_planes;      // heatmap planes (hm)
     int wch;           // weights channel in the output pixel, -1 = none (prev-frame heatmap)
-    int rows;          // rows per tile
-    int tiles_per_band;  // tiles (of `rows` rows) handled by one CTA
-    int bands_per_img;
-    int plane_stride;  // rows*W + pad
+    int P;             // pixels per chunk (multiple of 4)
+    int cpi;           // chunks per image
+    long long n_chunks;
     int per_class;     // 1: heat plane = obj.cls (Profile N); 0: plane 0 (reference as shipped)
     int force_explicit;
     int off_class, off_roff, off_box, off_track;
-    int vec_ok;        // tile byte ranges are 16-byte aligned
+    int bulk;          // chunks are 16-byte aligned in global memory: stream them out with bulk async copies
+    int vec;           // chunks are 16-byte aligned: the plain-store path may use 128-bit stores
+    int dbg_skip;      // experiment knob (CVM_RENDER_SKIP): 1 = no splat, 2 = no store, 4 = no fill
     double R, alpha;
 };
 
-// derived per-object quantities, computed once per tile by one thread per object
+// derived per-object quantities, computed once per image by one thread per object
 struct ObjDerived {
     double inv2vx, inv2vy;  // 1/(2*var)
     double rw;              // reduce_weight (processor.py:24)
@@ -52,6 +64,8 @@ struct ObjDerived {
     float offx, offy, bw, bh, tx, ty;
     int cls;
     int last_at_pixel;      // no later object scatters to the same pixel
+    int tab;                // start of the object's column factors in the table, -1 if they did not fit
+    int tabr;               // start of the object's row factors in the table, -1 if they did not fit
 };
 
 __device__ __forceinline__ void derive(const cvm_obj& o, const RenderParams& p, ObjDerived& d) {
@@ -102,237 +116,341 @@ __device__ __forceinline__ void derive(const cvm_obj& o, const RenderParams& p, 
     d.last_at_pixel = 1;
 }
 
-__global__ void __launch_bounds__(kThreads, 3) render_kernel(const RenderParams p) {
-    extern __shared__ __align__(16) float planes[];  // [n_planes + 1][plane_stride]; last = weights
-    __shared__ ObjDerived sobj[kMaxObjSmem];
-    __shared__ int s_list[kMaxObjSmem];
-    __shared__ int s_nlist;
-
-    const int tid = threadIdx.x;
-    const int b = blockIdx.x / p.bands_per_img;
-    const int band = blockIdx.x - b * p.bands_per_img;
-    const int W = p.W, PS = p.plane_stride;
-    const int Cout = p.Cout, hm = p.n_planes, wch = p.wch;
-    float* const wplane = planes + (size_t)hm * PS;
-    const int band_ya = band * p.tiles_per_band * p.rows;
-    const int band_yb = min(p.H, band_ya + p.tiles_per_band * p.rows);
-
-    const int o_begin = p.obj_offsets[b], o_end = p.obj_offsets[b + 1];
-    float* const out_img = p.out + (size_t)b * p.H * W * Cout;
-    const bool single_chunk = (o_end - o_begin) <= kMaxObjSmem;
-    int loaded_base = -1;  // which chunk of objects currently sits in sobj
-    if (single_chunk && o_end > o_begin) {  // the common case: derive once per band, reuse for every tile
-        if (tid < o_end - o_begin) derive(p.objs[o_begin + tid], p, sobj[tid]);
-        loaded_base = o_begin;
-    }
-
-    // compose mapping (vector path): the NHWC pattern repeats every 4 pixels = Cout float4s.  Thread t < NA handles float4
-    // slot r = t % Cout of pixel groups g = t / Cout, + GS, ...; which plane/pixel feeds its 4 floats never changes, so the
-    // loop is four shared loads through four pointers that advance by a fixed step (step 0 on a zero word for the
-    // channels that are always zero) and one 128-bit store.
-    __shared__ float s_zero[4];
-    if (tid < 4) s_zero[tid] = 0.f;
-    const int GS = kThreads / Cout, NA = GS * Cout;
-    const int cg0 = tid / Cout;
-    const float* csrc[4];
-    int cinc[4];
-    {
-        const int cr = tid - cg0 * Cout;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int f = 4 * cr + k, pig = f / Cout, ch = f - pig * Cout;
-            csrc[k] = s_zero;
-            cinc[k] = 0;
-            if (ch < hm || ch == wch) {
-                csrc[k] = planes + (ch < hm ? ch : hm) * PS + pig + 4 * cg0;
-                cinc[k] = 4 * GS;
-            }
-        }
-    }
-    // ignore boxes of this image, cached once per band (processor.py:318-323)
-    __shared__ int s_ign[kMaxIgnSmem][4];   // sx, ex, sy, ey (clamped)
-    int n_ign = 0, i_begin = 0;
-    if (p.ignore != nullptr && wch >= 0) {
-        i_begin = p.ign_offsets[b];
-        n_ign = p.ign_offsets[b + 1] - i_begin;
-        if (tid < min(n_ign, kMaxIgnSmem)) {
-            const cvm_box bx = p.ignore[i_begin + tid];
-            s_ign[tid][0] = max((int)bx.x, 0);
-            s_ign[tid][1] = min(max((int)(bx.x + bx.w), 0), W);
-            s_ign[tid][2] = max((int)bx.y, 0);
-            s_ign[tid][3] = min(max((int)(bx.y + bx.h), 0), p.H);
-        }
-    }
-
-    for (int ya = band_ya; ya < band_yb; ya += p.rows) {
-        const int yb = min(band_yb, ya + p.rows);
-        const int nrows = yb - ya;
-
-        // ---- init: heat = 0, weights = 1 (processor.py:267-268) ----
-        {
-            float4* p4 = reinterpret_cast<float4*>(planes);
-            const int n4 = (hm * PS) >> 2;
-            for (int i = tid; i < n4; i += kThreads) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int i = (n4 << 2) + tid; i < hm * PS; i += kThreads) planes[i] = 0.f;
-            for (int i = tid; i < PS; i += kThreads) wplane[i] = 1.f;
-            if (tid == 0) s_nlist = 0;
-        }
-        __syncthreads();  // planes are handed over from linear-index owners to column owners
-
-        // ---- splat: each thread owns columns x with x % 256 == tid for all rows of the tile ----
-        for (int base = o_begin; base < o_end; base += kMaxObjSmem) {
-            const int n = min(kMaxObjSmem, o_end - base);
-            if (loaded_base != base) {  // only with more than one chunk of objects
-                __syncthreads();
-                if (tid < n) derive(p.objs[base + tid], p, sobj[tid]);
-                loaded_base = base;
-                if (tid == 0) s_nlist = 0;
-                __syncthreads();
-            }
-            if (tid < n) {  // objects whose window touches this tile (order is irrelevant for max/min)
-                const ObjDerived& d = sobj[tid];
-                if (max(d.y0, ya) < min(d.y1, yb) && d.x0 < d.x1) s_list[atomicAdd(&s_nlist, 1)] = tid;
-            }
-            __syncthreads();
-            const int nl = s_nlist;
-            for (int li = 0; li < nl; ++li) {
-                const ObjDerived& d = sobj[s_list[li]];
-                const int r0 = max(d.y0, ya), r1 = min(d.y1, yb);
-                float* const hp = planes + (size_t)d.plane * PS;
-                for (int x = d.x0 + ((tid - d.x0) & (kThreads - 1)); x < d.x1; x += kThreads) {
-                    const double dx = (double)(x - d.cx);
-                    const double ax = dx * dx * d.inv2vx;
-                    for (int y = r0; y < r1; ++y) {
-                        const double dy = (double)(y - d.cy);
-                        const double g = exp(-(ax + dy * dy * d.inv2vy));                 // processor.py:34-36
-                        const int idx = (y - ya) * W + x;
-                        hp[idx] = fmaxf(hp[idx], (float)(g * d.peak));                    // :37
-                        if (wch >= 0) wplane[idx] = fminf(wplane[idx], (float)(1.0 - d.rw * g));   // :38
-                    }
-                }
-            }
-        }
-
-        // ---- ignore areas: weights = 0, input-px numbers used as mask indices (processor.py:318-323) ----
-        for (int i = 0; i < n_ign; ++i) {
-            int sx, ex, sy, ey;
-            if (i < kMaxIgnSmem) {
-                sx = s_ign[i][0], ex = s_ign[i][1], sy = s_ign[i][2], ey = s_ign[i][3];
-            } else {
-                const cvm_box bx = p.ignore[i_begin + i];
-                sx = max((int)bx.x, 0), ex = min(max((int)(bx.x + bx.w), 0), W);
-                sy = max((int)bx.y, 0), ey = min(max((int)(bx.y + bx.h), 0), p.H);
-            }
-            const int r0 = max(sy, ya), r1 = min(ey, yb);
-            for (int x = sx + ((tid - sx) & (kThreads - 1)); x < ex; x += kThreads)   // same column ownership as the splat
-                for (int y = r0; y < r1; ++y) wplane[(y - ya) * W + x] = 0.f;
-        }
-        __syncthreads();
-
-        // ---- compose NHWC and stream out ----
-        const int tile_floats = nrows * W * Cout;
-        float* const out_tile = out_img + (size_t)ya * W * Cout;
-        if (p.vec_ok && ((nrows * W) & 3) == 0) {  // a ragged last tile may not be whole groups of 4 pixels
-            if (tid < NA) {
-                const int n_groups = (nrows * W) >> 2;
-                float4* dst = reinterpret_cast<float4*>(out_tile) + tid;
-                const float *s0 = csrc[0], *s1 = csrc[1], *s2 = csrc[2], *s3 = csrc[3];
-                for (int g = cg0; g < n_groups; g += GS, dst += NA) {
-                    st_cs_f4(dst, make_float4(*s0, *s1, *s2, *s3));
-                    s0 += cinc[0];
-                    s1 += cinc[1];
-                    s2 += cinc[2];
-                    s3 += cinc[3];
-                }
-            }
-        } else {
-            for (int f = tid; f < tile_floats; f += kThreads) {
-                const int px = f / Cout, ch = f - px * Cout;
-                out_tile[f] = ch < hm ? planes[(size_t)ch * PS + px] : (ch == wch ? wplane[px] : 0.f);
-            }
-        }
-        __syncthreads();  // the planes are re-initialised for the next tile
-    }
-
-    // ---- centre scatter (processor.py:288-299): patched after the band is out; last object wins per pixel ----
-    if (p.off_class < 0 && p.off_roff < 0 && p.off_box < 0 && p.off_track < 0) return;
-    for (int base = o_begin; base < o_end; base += kMaxObjSmem) {
-        const int n = min(kMaxObjSmem, o_end - base);
-        if (loaded_base != base) {
-            __syncthreads();
-            if (tid < n) derive(p.objs[base + tid], p, sobj[tid]);
-            loaded_base = base;
-            __syncthreads();
-        }
-        if (tid < n) {
-            const ObjDerived& d = sobj[tid];
-            if (d.scy >= band_ya && d.scy < band_yb && d.scx >= 0) {
-                // a later object (list order) at the same pixel overwrites r_offset/fullbox/track
-                bool last = true;
-                for (int j = base + tid + 1; j < o_end && last; ++j) {
-                    if (j - base < n) {
-                        const ObjDerived& e = sobj[j - base];
-                        if (e.scx == d.scx && e.scy == d.scy) last = false;
-                    } else {
-                        ObjDerived e;
-                        derive(p.objs[j], p, e);
-                        if (e.scx == d.scx && e.scy == d.scy) last = false;
-                    }
-                }
-                float* px = out_img + ((size_t)d.scy * W + d.scx) * Cout;
-                if (p.off_class >= 0 && d.cls >= 0 && p.off_class + d.cls < Cout) px[p.off_class + d.cls] = 1.0f;   // :290
-                if (last) {
-                    if (p.off_roff >= 0) {
-                        px[p.off_roff] = d.offx;                                                                   // :292
-                        px[p.off_roff + 1] = d.offy;
-                    }
-                    if (p.off_box >= 0) {
-                        px[p.off_box] = d.bw;                                                                      // :294
-                        px[p.off_box + 1] = d.bh;
-                    }
-                    if (p.off_track >= 0) {
-                        px[p.off_track] = d.tx;
-                        px[p.off_track + 1] = d.ty;
-                    }
-                }
-            }
-        }
-    }
+// shared -> global bulk copy (bytes % 16 == 0, both addresses 16-byte aligned), tracked by the issuing thread's bulk groups
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-int pick_rows(int H, int W, int n_planes_total, size_t* smem_bytes, int* plane_stride) {
-    // as many rows as keep the planes <= ~36 KB (>= 4 CTAs/SM by shared memory), at least one
-    int rows = 1;
-    const size_t budget = 36 * 1024;
-    while (rows < H && (size_t)(rows * 2) * W * n_planes_total * 4 <= budget) rows *= 2;
-    *plane_stride = ((rows * W + 3) & ~3) + 1;   // odd stride: plane-to-plane bank offset of 1
-    *smem_bytes = (size_t)(*plane_stride) * n_planes_total * 4 + 16;
-    return rows;
+extern __shared__ __align__(128) unsigned char g_render_smem[];   // two staging buffers of kChunkBytes
+
+// max / min combine of a float into shared memory through integer atomics on the bit pattern: non-negative floats order
+// like signed ints, negative floats order inversely like unsigned ints, and each of the two operations keeps the cell
+// monotone in float order, so any interleaving of them ends at the true max / min.
+__device__ __forceinline__ void smem_max_float(float* cell, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(cell), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(cell), __float_as_uint(v));
+}
+__device__ __forceinline__ void smem_min_float(float* cell, float v) {
+    if (v >= 0.f) atomicMin(reinterpret_cast<int*>(cell), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned int*>(cell), __float_as_uint(v));
+}
+
+// The gaussian is separable: exp(-(ax + ay)) = exp(-ax) * exp(-ay).  The column factors exp(-ax) of every object are
+// and its row factors exp(-ay) are tabulated once per image, so a covered pixel costs one fp64 multiply instead
+// of one fp64 exp.  The product differs from the exp of the sum by a few ulp of a DOUBLE; after the rounding to fp32
+// that the reference stores, the value is the same except when a rounding boundary falls inside that interval
+// (probability ~1e-8 per value), where it differs by one fp32 ulp -- far inside the 1e-5 tolerance.
+__global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_constant__ RenderParams p) {
+    __shared__ ObjDerived sobj[kMaxObjSmem];
+    __shared__ double s_col[kColTab];                   // column factors, object after object
+    __shared__ double s_row[kRowTab];                   // row factors, object after object
+    __shared__ int s_unit[kMaxUnits];                   // work units: object (low 8 bits) | 32-column segment of its window
+    __shared__ int s_nunits[2];                         // double-buffered by list-build parity (reset one build ahead)
+    __shared__ int s_ign[kMaxIgnSmem][4];               // ignore boxes of the image: sx, ex, sy, ey (clamped to the map)
+    __shared__ unsigned char s_own[kColTab + kRowTab];   // object that owns each table entry
+    __shared__ int s_used[2];                            // table entries in use (columns, rows)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = p.W, HW = p.HW, Cout = p.Cout, wch = p.wch, P = p.P, cpi = p.cpi;
+    const bool has_w = wch >= 0;
+    float* const stage0 = reinterpret_cast<float*>(g_render_smem);
+
+    const long long G = gridDim.x, g = blockIdx.x;
+    const long long c0 = g * p.n_chunks / G, c1 = (g + 1) * p.n_chunks / G;
+    long long img = c0 / cpi;
+    int ci = (int)(c0 - img * cpi);
+    int ya = (ci * P) / W, xa = ci * P - ya * W;   // row / column of the chunk's first pixel, kept incrementally
+    // pattern fill: thread t < n_fill writes the float4s t, t + n_fill, ...; n_fill is a multiple of Cout, so the channel
+    // phase of its float4 -- and with it the value (zeros, 1.0 where the weights channel falls) -- never changes
+    const int n_fill = (kThreads / Cout) * Cout;
+    float4 fill_v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_w) {
+        const int r = (4 * tid) % Cout;   // channel of the first float of this thread's float4s
+        fill_v.x = ((r + 0) % Cout == wch) ? 1.f : 0.f;
+        fill_v.y = ((r + 1) % Cout == wch) ? 1.f : 0.f;
+        fill_v.z = ((r + 2) % Cout == wch) ? 1.f : 0.f;
+        fill_v.w = ((r + 3) % Cout == wch) ? 1.f : 0.f;
+    }
+    const bool scatter = p.off_class >= 0 || p.off_roff >= 0 || p.off_box >= 0 || p.off_track >= 0;
+    long long loaded_img = -1;   // image whose objects the batch in sobj belongs to
+    int loaded_base = -1;        // first object of that batch
+    long long ign_img = -1;      // image whose ignore boxes sit in s_ign
+    long long off_img = -1;      // image whose ranges are in the registers below
+    int o_begin = 0, o_end = 0, i_begin = 0, n_ign = 0;
+    int buf = 0;
+    int lk = 0;                  // list builds so far (parity picks the counter)
+    if (tid < 2) s_nunits[tid] = 0;
+    __syncthreads();
+
+    for (long long c = c0; c < c1; ++c) {
+        const int q0 = ci * P, q1 = min(HW, q0 + P), npx = q1 - q0;
+        int yb = ya;   // row of the chunk's last pixel
+        for (int t = xa + npx - 1; t >= W; t -= W) ++yb;
+        float* const st = stage0 + (size_t)buf * (kChunkBytes / 4);
+        if (off_img != img) {   // object / ignore-box ranges of the image: fetched once per image, not once per chunk
+            o_begin = p.obj_offsets[img];
+            o_end = p.obj_offsets[img + 1];
+            n_ign = i_begin = 0;
+            if (p.ignore != nullptr && has_w) {
+                i_begin = p.ign_offsets[img];
+                n_ign = p.ign_offsets[img + 1] - i_begin;
+            }
+            off_img = img;
+        }
+        const int n_batches = (o_end - o_begin + kMaxObjSmem - 1) / kMaxObjSmem;
+
+        // ---- phase 1: pattern fill (heat = 0, weights = 1, regression targets = 0; processor.py:267-268) ----
+        if (tid < n_fill && !(p.dbg_skip & 4)) {
+            const int n4 = (npx * Cout + 3) >> 2;   // the buffer is a whole number of float4s
+            float4* s4 = reinterpret_cast<float4*>(st);
+            for (int f = tid; f < n4; f += n_fill) s4[f] = fill_v;
+        }
+        if (ign_img != img) {   // clamp the ignore boxes once per image (read after the barriers below)
+            if (tid < min(n_ign, kMaxIgnSmem)) {
+                const cvm_box bx = p.ignore[i_begin + tid];
+                s_ign[tid][0] = max((int)bx.x, 0);
+                s_ign[tid][1] = min(max((int)(bx.x + bx.w), 0), W);
+                s_ign[tid][2] = max((int)bx.y, 0);
+                s_ign[tid][3] = min(max((int)(bx.y + bx.h), 0), p.H);
+            }
+            ign_img = img;
+        }
+
+        for (int bi = 0; bi < n_batches; ++bi) {   // one batch in the common case
+            const int base = o_begin + bi * kMaxObjSmem;
+            const int n = min(kMaxObjSmem, o_end - base);
+            const int par = (lk++) & 1;
+            if (loaded_img != img || loaded_base != base) {
+                // ---- once per image (and object batch): derived records, scatter winners, column factors ----
+                if (bi > 0) __syncthreads();   // the previous batch is still being read
+                if (tid < n) derive(p.objs[base + tid], p, sobj[tid]);
+                __syncthreads();
+                if (tid < n && scatter) {
+                    // a later object (list order) on the same centre pixel overwrites r_offset / fullbox / track_offset
+                    // (processor.py:288-299), so only the last one writes them
+                    const int sx = sobj[tid].scx, sy = sobj[tid].scy;
+                    bool last = true;
+                    for (int j = base + tid + 1; j < o_end && last; ++j) {
+                        if (j - base < n) {
+                            if (sobj[j - base].scx == sx && sobj[j - base].scy == sy) last = false;
+                        } else {
+                            ObjDerived e;
+                            derive(p.objs[j], p, e);
+                            if (e.scx == sx && e.scy == sy) last = false;
+                        }
+                    }
+                    sobj[tid].last_at_pixel = last;
+                }
+                if (tid < n) {   // table space in object order; an object that does not fit evaluates exp per pixel
+                    int off = 0, offr = 0;
+                    for (int o = 0; o < tid; ++o) {
+                        off += max(0, sobj[o].x1 - sobj[o].x0);
+                        offr += max(0, sobj[o].y1 - sobj[o].y0);
+                    }
+                    const int wd = max(0, sobj[tid].x1 - sobj[tid].x0), ht = max(0, sobj[tid].y1 - sobj[tid].y0);
+                    const int tab = off + wd <= kColTab ? off : -1, tabr = offr + ht <= kRowTab ? offr : -1;
+                    // owner of every table entry, so that the factors can be computed one entry per thread
+                    if (tab >= 0)
+                        for (int k = 0; k < wd; ++k) s_own[tab + k] = (unsigned char)tid;
+                    if (tabr >= 0)
+                        for (int k = 0; k < ht; ++k) s_own[kColTab + tabr + k] = (unsigned char)tid;
+                    if (tid == n - 1) {
+                        s_used[0] = tab >= 0 ? tab + wd : 0;      // (the last object fits only if all before it did)
+                        s_used[1] = tabr >= 0 ? tabr + ht : 0;
+                    }
+                    sobj[tid].tab = tab;
+                    sobj[tid].tabr = tabr;
+                }
+                __syncthreads();
+                if (sobj[n - 1].tab < 0 || sobj[n - 1].tabr < 0) {
+                    // some object did not fit: its entries are not tabulated, the entries before it are found by scanning
+                    if (tid == 0) {
+                        int used = 0, usedr = 0;
+                        for (int o = 0; o < n; ++o) {
+                            if (sobj[o].tab >= 0) used = sobj[o].tab + max(0, sobj[o].x1 - sobj[o].x0);
+                            if (sobj[o].tabr >= 0) usedr = sobj[o].tabr + max(0, sobj[o].y1 - sobj[o].y0);
+                        }
+                        s_used[0] = used;
+                        s_used[1] = usedr;
+                    }
+                    __syncthreads();
+                }
+                {
+                    const int used = s_used[0], usedr = s_used[1];
+                    for (int e = tid; e < used + usedr; e += kThreads) {
+                        if (e < used) {
+                            const ObjDerived& d = sobj[s_own[e]];
+                            const double dx = (double)(d.x0 + (e - d.tab) - d.cx);
+                            s_col[e] = exp(-(dx * dx * d.inv2vx));
+                        } else {
+                            const int r = e - used;
+                            const ObjDerived& d = sobj[s_own[kColTab + r]];
+                            const double dy = (double)(d.y0 + (r - d.tabr) - d.cy);
+                            s_row[r] = exp(-(dy * dy * d.inv2vy));
+                        }
+                    }
+                }
+                loaded_img = img;
+                loaded_base = base;
+            }
+            // ---- work units of this chunk ----
+            if (tid < n && !(p.dbg_skip & 32)) {
+                const ObjDerived& d = sobj[tid];
+                if (max(d.y0, ya) < min(d.y1, yb + 1) && d.x0 < d.x1) {
+                    const int u = (d.x1 - d.x0 + 31) >> 5;
+                    const int start = atomicAdd(&s_nunits[par], u);
+                    for (int k = 0; k < u && start + k < kMaxUnits; ++k) s_unit[start + k] = tid | (k << 8);
+                }
+            }
+            if (tid == 0) s_nunits[par ^ 1] = 0;   // the other counter is idle: reset it for the next build
+            __syncthreads();   // ---- barrier A: fill, tables and units are visible ----
+
+            // ---- phase 2: one warp per (unit, row) item, lane = column; max/min-combine with shared atomics (windows of
+            //      different objects overlap).  Items are dealt round-robin to the warps; order is irrelevant ----
+            const int total = s_nunits[par];
+            const bool overflow = total > kMaxUnits;   // absurdly many wide objects: whole-object items instead
+            const int n_items = (p.dbg_skip & 1) ? 0 : (overflow ? n : total);
+            for (int it = warp; it < n_items; it += kWarps) {
+                const int u = overflow ? it : s_unit[it];
+                const ObjDerived& d = sobj[u & 255];
+                if (d.x0 >= d.x1) continue;
+                int xs = d.x0, xe = d.x1;
+                if (!overflow) {
+                    xs = d.x0 + ((u >> 8) << 5);
+                    xe = min(d.x1, xs + 32);
+                }
+                const int r0 = max(d.y0, ya), r1 = min(d.y1, yb + 1);
+                for (int x = xs + lane; x < xe; x += 32) {
+                    double ex;
+                    if (d.tab >= 0) {
+                        ex = s_col[d.tab + (x - d.x0)];
+                    } else {
+                        const double dx = (double)(x - d.cx);
+                        ex = exp(-(dx * dx * d.inv2vx));
+                    }
+                    for (int y = r0; y < r1; ++y) {
+                        const int q = y * W + x;
+                        if (q < q0 || q >= q1) continue;   // the chunk may start / end inside a row
+                        double ey;
+                        if (d.tabr >= 0) {
+                            ey = s_row[d.tabr + (y - d.y0)];
+                        } else {
+                            const double dy = (double)(y - d.cy);
+                            ey = exp(-(dy * dy * d.inv2vy));
+                        }
+                        const double gv = ex * ey;                                           // processor.py:34-36
+                        float* const px = st + (size_t)(q - q0) * Cout;
+                        smem_max_float(px + d.plane, (float)(gv * d.peak));                   // :37
+                        if (has_w) smem_min_float(px + wch, (float)(1.0 - d.rw * gv));        // :38
+                    }
+                }
+            }
+            // centre scatter: regression targets and the class one-hot live in channels the splat never touches
+            if (scatter && tid < n && !(p.dbg_skip & 64)) {
+                const ObjDerived& d = sobj[tid];
+                const int qs = d.scy * W + d.scx;
+                if (d.scx >= 0 && qs >= q0 && qs < q1) {
+                    float* px = st + (size_t)(qs - q0) * Cout;
+                    if (p.off_class >= 0 && d.cls >= 0 && p.off_class + d.cls < Cout) px[p.off_class + d.cls] = 1.0f;   // :290
+                    if (d.last_at_pixel) {
+                        if (p.off_roff >= 0) {
+                            px[p.off_roff] = d.offx;                                                                   // :292
+                            px[p.off_roff + 1] = d.offy;
+                        }
+                        if (p.off_box >= 0) {
+                            px[p.off_box] = d.bw;                                                                      // :294
+                            px[p.off_box + 1] = d.bh;
+                        }
+                        if (p.off_track >= 0) {
+                            px[p.off_track] = d.tx;
+                            px[p.off_track + 1] = d.ty;
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- phase 3: ignore areas: weights = 0, input-px numbers used as mask indices (processor.py:318-323) ----
+        bool ign_hit = n_ign > kMaxIgnSmem || (n_ign > 0 && n_batches == 0);   // (boxes beyond the cache / no barrier yet: take the slow way)
+        for (int i = 0; i < ((p.dbg_skip & 128) ? 0 : min(n_ign, kMaxIgnSmem)) && !ign_hit; ++i)
+            ign_hit = s_ign[i][0] < s_ign[i][1] && max(s_ign[i][2], ya) < min(s_ign[i][3], yb + 1);
+        if (ign_hit) {   // uniform: few chunks meet an ignore box
+            __syncthreads();   // all splats are in (and s_ign is visible when the image had no objects)
+            for (int i = 0; i < n_ign; ++i) {
+                int sx, ex, sy, ey;
+                if (i < kMaxIgnSmem) {
+                    sx = s_ign[i][0], ex = s_ign[i][1], sy = s_ign[i][2], ey = s_ign[i][3];
+                } else {
+                    const cvm_box bx = p.ignore[i_begin + i];
+                    sx = max((int)bx.x, 0), ex = min(max((int)(bx.x + bx.w), 0), W);
+                    sy = max((int)bx.y, 0), ey = min(max((int)(bx.y + bx.h), 0), p.H);
+                }
+                sy = max(sy, ya);
+                ey = min(ey, yb + 1);
+                const int bw = ex - sx, cells = bw * (ey - sy);
+                if (bw <= 0 || ey <= sy) continue;
+                for (int k = tid; k < cells; k += kThreads) {
+                    const int yy = sy + k / bw, xx = sx + k % bw, q = yy * W + xx;
+                    if (q >= q0 && q < q1) st[(size_t)(q - q0) * Cout + wch] = 0.f;
+                }
+            }
+        }
+
+        // ---- stream the chunk out ----
+        float* const dst = p.out + ((size_t)img * HW + q0) * Cout;
+        if (p.bulk) {
+            if (!(p.dbg_skip & 16)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk engine
+            // the next chunk refills the other buffer right after the barrier: its bulk store must have finished reading
+            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncthreads();   // ---- barrier B ----
+            if (tid == 0 && !(p.dbg_skip & 2)) bulk_s2g(dst, st, (uint32_t)(npx * Cout * 4));
+        } else {
+            __syncthreads();
+            const int nf = npx * Cout;
+            if (p.vec) {   // 16-byte aligned chunk: 128-bit streaming stores
+                const float4* s4 = reinterpret_cast<const float4*>(st);
+                float4* d4 = reinterpret_cast<float4*>(dst);
+                for (int f = tid; f < (nf >> 2); f += kThreads) st_cs_f4(d4 + f, s4[f]);
+            } else {
+                for (int f = tid; f < nf; f += kThreads) dst[f] = st[f];
+            }
+            __syncthreads();   // the buffer is refilled two chunks later, but sobj / lists are reused by the next one
+        }
+        buf ^= 1;
+        if (++ci == cpi) {
+            ci = 0;
+            ++img;
+            ya = xa = 0;
+        } else {
+            for (xa += P; xa >= W; xa -= W) ++ya;
+        }
+    }
+    if (p.bulk && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA retires
 }
 
 int launch_render(const RenderParams& p0, int B, cudaStream_t st) {
     RenderParams p = p0;
-    size_t smem = 0;
-    p.rows = pick_rows(p.H, p.W, p.n_planes + 1, &smem, &p.plane_stride);
-    if (smem > 200 * 1024) {
-        cvm_set_error("render: one row of %d planes x %d px does not fit in shared memory", p.n_planes + 1, p.W);
-        return CVM_ERR_ARG;
-    }
-    // a CTA renders a band of consecutive tiles of one image (object records are derived once per band); bands are sized so
-    // that the grid still fills the machine ~4x over
-    const int tiles_per_img = (p.H + p.rows - 1) / p.rows;
-    int tpb = 8;
-    const long long want = 4LL * cvm_num_sms() * 4;
-    while (tpb > 1 && (long long)B * ((tiles_per_img + tpb - 1) / tpb) < want) tpb >>= 1;
-    p.tiles_per_band = tpb;
-    p.bands_per_img = (tiles_per_img + tpb - 1) / tpb;
-    // 128-bit stores need every tile start (and the image start) 16-byte aligned and whole groups of 4 pixels per tile
-    p.vec_ok = cvm_aligned16(p.out) && (((long long)p.rows * p.W) % 4 == 0) && (((long long)p.H * p.W * p.Cout) % 4 == 0) &&
-               p.Cout <= kThreads;
+    p.HW = p.H * p.W;
+    int P = (kChunkBytes / (p.Cout * 4)) & ~3;
+    if (P > 4096) P = 4096;   // keeps the (object, row) items of a chunk short for narrow outputs (prev-frame heatmap)
+    if (P > ((p.HW + 3) & ~3)) P = (p.HW + 3) & ~3;
+    CVM_CHECK_ARG(P >= 4 && p.Cout <= kThreads, "render: %d output channels do not fit the staging buffer", p.Cout);
+    p.P = P;
+    p.cpi = (p.HW + P - 1) / P;
+    p.n_chunks = (long long)B * p.cpi;
+    if (p.n_chunks == 0) return CVM_OK;
+    // bulk stores need 16-byte granules: base aligned, every image a whole number of them (chunks are P*Cout*4 bytes with
+    // P % 4 == 0, the partial last chunk of an image then ends on a granule too)
+    p.bulk = cvm_aligned16(p.out) && (((long long)p.HW * p.Cout) % 4 == 0);
+    p.vec = p.bulk;
+    if (const char* e = getenv("CVM_RENDER_SKIP")) p.dbg_skip = atoi(e);
+    if (p.dbg_skip & 8) p.bulk = 0;   // experiment: plain stores instead of bulk copies
+    const size_t smem = 2 * (size_t)kChunkBytes;
     CVM_CHECK_CUDA(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long grid = (long long)B * p.bands_per_img;
-    if (grid == 0) return CVM_OK;
-    CVM_CHECK_ARG(grid < 2147483647LL, "render grid too large");
+    long long grid = 2LL * cvm_num_sms();
+    if (grid > p.n_chunks) grid = p.n_chunks;
     render_kernel<<<(unsigned)grid, kThreads, smem, st>>>(p);
     CVM_CHECK_LAUNCH("render_kernel");
     return CVM_OK;

@@ -1,0 +1,34 @@
+import os, sys
+sys.path.insert(0, "/root/repo/computer-vision-models_b200"); sys.path.insert(0, "/root/repo")
+import numpy as np, torch
+import bench
+from cvmhot import ops
+from cvmhot.layout import layout_from_params
+from cvmhot.models.centernet import CenternetParams
+from cvmhot.models.centernet.processor import pack_boxes, pack_objects
+B = 256
+p = CenternetParams(10, per_class_heatmap=True); p.INPUT_HEIGHT, p.INPUT_WIDTH = 256, 768
+L = layout_from_params(p)
+dev = torch.device("cuda", 0)
+boxes, cls, ign = bench.gen_objects(0, B)
+rec, offs = pack_objects(list(boxes), list(cls)); ign_rec, ign_offs = pack_boxes(list(ign))
+objs_d = ops.to_device_records(rec, ops.OBJ_DTYPE, dev); offs_d = torch.from_numpy(offs).to(dev)
+ign_d = ops.to_device_records(ign_rec, ops.BOX_DTYPE, dev); ioffs_d = torch.from_numpy(ign_offs).to(dev)
+y1 = torch.empty((B, 128, 384, L.Ct), device=dev); y2 = torch.empty_like(y1)
+def run(tag):
+    for _ in range(3): ops.render_gt(L, objs_d, offs_d, B, ign_d, ioffs_d, out=y1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 10
+    e0.record()
+    for i in range(n): ops.render_gt(L, objs_d, offs_d, B, ign_d, ioffs_d, out=y1 if i % 2 else y2)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    print(f"{tag:30s} {ms:.4f} ms  {y1.numel()*4/ms/1e6:.0f} GB/s", flush=True)
+for env in sys.argv[1:]:
+    for kv in env.split(","):
+        if kv != "-":
+            k, v = kv.split("="); os.environ[k] = v
+    run(env)
+    for kv in env.split(","):
+        if kv != "-": os.environ.pop(kv.split("=")[0])
