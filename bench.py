@@ -91,6 +91,15 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def load_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed `ncu --set full` capture
+    of this same workload (profiles/traffic.json, written by profiles/ncu_traffic.py); None if not captured."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel)
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -99,46 +108,82 @@ def load_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_port_step(n_images, first_image=0):
-    """The oracle port of the path on `n_images` images of the same workload; returns seconds (render, loss, decode)."""
-    from oracle import decode_np, loss_np, render_np
+def _port_inputs(first_image, n_images):
     from oracle.layout import make_layout
     Lo = make_layout(H, W, NB_CLASSES, "N")
     boxes, cls, ign = gen_objects(first_image, n_images)
-    rng = np.random.default_rng(99)
+    rng = np.random.default_rng(99 + first_image)
     yp = np.zeros((n_images, H, W, Lo.Cp), np.float32)
     yp[..., :NB_CLASSES] = 1.0 / (1.0 + np.exp(-rng.normal(-4.0, 1.5, (n_images, H, W, NB_CLASSES))))
     yp[..., NB_CLASSES:] = rng.uniform(0, 60, (n_images, H, W, Lo.Cp - NB_CLASSES))
+    return Lo, boxes, cls, ign, yp
+
+
+def cpu_port_step(n_images, first_image=0, inputs=None):
+    """The oracle port of the path on `n_images` images of the same workload; returns seconds (render, loss, decode)
+    and the loss partials of these images."""
+    from oracle import decode_np, loss_np, render_np
+    Lo, boxes, cls, ign, yp = inputs if inputs is not None else _port_inputs(first_image, n_images)
     t0 = time.perf_counter()
     yt = np.stack([render_np.render_image(Lo, boxes[i], cls[i], ign[i]) for i in range(n_images)])
     t1 = time.perf_counter()
-    loss_np.total_loss(Lo, yt, yp)
+    part = loss_np.partials(Lo, yt, yp, True)
     t2 = time.perf_counter()
     decode_np.decode_topk(Lo, yp, TOPK)
     t3 = time.perf_counter()
-    return t1 - t0, t2 - t1, t3 - t2
+    return (t1 - t0, t2 - t1, t3 - t2), np.asarray(part, np.float64)
+
+
+_WORKER_INPUTS = {}
+
+
+def _port_worker(task):
+    """One host core's share of a reference-arm step (images are independent; the loss partials are summed by the parent,
+    which is the same exchange the GPUs do)."""
+    first, n = task
+    return cpu_port_step(n, first, _WORKER_INPUTS[(first, n)])   # inputs were generated by the parent before the fork
 
 
 def run_reference(args):
-    """Reference arm: the CPU port on the host cores.  Under torchrun only rank 0 works."""
+    """Reference arm: the reference's CPU implementation of the path on the host cores.  The reference itself (pure
+    Python on TensorFlow/numba, no setup.py) can be neither installed nor carried to the GPU box, so this is the oracle
+    port, spread over all host cores.  Under torchrun only rank 0 works."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    n = 8  # bounded sample per step: BASELINE configs[0]'s batch
-    for _ in range(args.warmup):
-        cpu_port_step(n)
-    ts = [cpu_port_step(n) for _ in range(args.steps)]
-    tot = float(np.sum(ts))
+    import multiprocessing as mp
+    from oracle import loss_np
+    from oracle.layout import make_layout
+    cores = max(1, os.cpu_count() or 1)
+    per_core = 2
+    n = cores * per_core  # bounded sample per step
+    tasks = [(i * per_core, per_core) for i in range(cores)]
+    Lo = make_layout(H, W, NB_CLASSES, "N")
+    for t in tasks:                                          # synthetic inputs: generated once, outside the timed region
+        _WORKER_INPUTS[t] = _port_inputs(*t)
+    with mp.get_context("fork").Pool(cores) as pool:
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_port_worker, tasks, chunksize=1)
+        t0 = time.perf_counter()
+        stage = np.zeros(3)
+        for _ in range(args.steps):
+            res = pool.map(_port_worker, tasks, chunksize=1)
+            part = np.sum([r[1] for r in res], axis=0)      # the one exchange of the path, then the finalise step
+            loss = loss_np.finalize(Lo, part.tolist())[0]
+            stage += np.sum([r[0] for r in res], axis=0)
+        tot = time.perf_counter() - t0
     value = n * args.steps / tot
     line = {
         "impl": "reference", "metric": "images/sec (heatmap render+loss+decode)", "value": value, "unit": "images/sec",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * tot / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CenterNet 2D-OD full heatmap path (render+loss+decode), 10-class 128x384, 32 obj/img, top-K=100",
+        "config": {"workload": "CenterNet 2D-OD full heatmap path (render+loss+decode), 10-class 128x384, 32 obj/img, top-K=100 (BASELINE configs[1])",
                    "batch_per_step": n, "note": "bounded sample of configs[1] (same per-image work)"},
-        "cpu_baseline": {"value": value, "unit": "images/sec", "cores": 1, "kind": "port",
-                         "sample": f"{n} images/step x {args.steps} steps, NumPy oracle port (TF/numba reference cannot run on the box)"},
+        "cpu_baseline": {"value": value, "unit": "images/sec", "cores": cores, "kind": "port",
+                         "sample": f"{n} images/step x {args.steps} steps, NumPy oracle port over {cores} worker processes "
+                                   "(the TF/numba reference cannot be installed or carried to the box)"},
         "e2e": {"value": value, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "stages_s_per_image": {k: float(np.sum([t[i] for t in ts]) / (n * args.steps)) for i, k in enumerate(("render", "loss", "decode"))},
+        "stages_core_s_per_image": {k: float(stage[i] / (n * args.steps)) for i, k in enumerate(("render", "loss", "decode"))},
+        "loss": float(loss),
     }
     print(json.dumps(line), flush=True)
 
@@ -285,7 +330,7 @@ def run_ours(args):
     value = world * B * args.steps / (elapsed_ms * 1e-3)
     e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
     peak_gbs, peak_src = load_peaks()
-    names = ["render_kernel", "loss_fwd_kernel", "decode_stream_kernel"]
+    names = ["render_kernel", "loss_fwd_fast_kernel", "decode_scan_kernel"]
     sbytes = [bytes_render, bytes_loss, bytes_decode]
     dom = int(np.argmax(stage_ms))
     achieved = sbytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
@@ -296,7 +341,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         n_cpu = 8
         cpu_port_step(1)
-        ts = cpu_port_step(n_cpu)
+        ts, _ = cpu_port_step(n_cpu)
         cpu = {"value": n_cpu / sum(ts), "unit": "images/sec", "cores": 1, "kind": "port",
                "sample": f"{n_cpu} images of the same workload (configs[0] batch), NumPy oracle port; "
                          f"render {ts[0]:.2f}s loss {ts[1]:.2f}s decode {ts[2]:.2f}s"}
@@ -309,7 +354,7 @@ def run_ours(args):
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world} (batch shards, one 128-byte all-reduce)",
                    "l2": "inputs larger than L2 (y_pred 705 MB + y_true 755 MB per GPU per step)"},
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak_gbs, "traffic": load_traffic(names[dom]), "peak_source": peak_src,
                      "whole_step_gbs": whole, "whole_step_frac": whole / peak_gbs,
                      "stages": {n: {"ms": float(m), "gbs": b / (m * 1e-3) / 1e9, "frac": b / (m * 1e-3) / 1e9 / peak_gbs}
                                 for n, m, b in zip(names, stage_ms, sbytes)}},
