@@ -39,7 +39,6 @@ constexpr int kSegKeys = 512;      // keys a segment may publish without an exac
 constexpr int kScoreShift = 19;    // score histogram: bin = float bits >> 19 (sign 0, 8 exponent bits, 4 mantissa bits)
 constexpr int kScoreBins = 1 << (31 - kScoreShift);
 constexpr int kMaxK = 1024;
-constexpr int kMaxAppend = 5120;   // T * hm: most candidates one step can append between two barriers
 constexpr int kMergeCap = 4096;    // merge kernel: keys buffered before an intermediate select
 constexpr int kSmemBudget = 227 * 1024 - 1024;
 
@@ -123,10 +122,8 @@ size_t smem_bytes(int S, int gran_floats, int cap, int K) {
 // named barrier over the first `nt` threads of the CTA (the scanner warps; the loader warp never joins)
 __device__ __forceinline__ void group_sync(int nt) { asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory"); }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
+__device__ __noinline__ void gather(const DecodeParams& p, bool at_segment_end, int seg);
 
 // ---- exact top-K select on distinct 64-bit keys held in shared memory -------------------------------------------------
 // On return keys[0..K) hold the K largest (unordered), *thr is the K-th largest key.  n > K required.  Called by the
@@ -303,6 +300,12 @@ __device__ __noinline__ void flush_segment(const DecodeParams& p, int seg) {
     group_sync(nt);
 }
 
+__device__ __forceinline__ uint2 load_ctrl(const SharedHead* h) {
+    uint2 v;
+    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_u32(&h->thr_bits)) : "memory");
+    return v;
+}
+
 // One lane's pixel that reached the threshold and waits for its 3x3 test.
 struct Hit {
     unsigned long long mask;   // heatmap channels whose score reached the threshold (0: no hit)
@@ -409,6 +412,10 @@ __device__ __forceinline__ void test_hits(const DecodeParams& p, long long img, 
                 atomicAdd(&shist[bin], 1u);
                 if ((int)bin > *(volatile int*)&h->maxbin) atomicMax(&h->maxbin, (int)bin);
             }
+            // Safe point after every batch of appends: once the buffer has passed its mark, a warp adds at most these
+            // <= 32 keys before it joins the compaction, which bounds the buffer (cap = mark + 32 per scanner warp).
+            __syncwarp();
+            if (__any_sync(0xffffffffu, load_ctrl(h).y != 0)) gather(p, false, 0);
         }
     }
 }
@@ -482,11 +489,6 @@ __device__ __noinline__ void gather(const DecodeParams& p, bool at_segment_end, 
 }
 
 
-__device__ __forceinline__ uint2 load_ctrl(const SharedHead* h) {
-    uint2 v;
-    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_u32(&h->thr_bits)) : "memory");
-    return v;
-}
 
 // Per-thread (warp-uniform) pipeline state of a scanner warp; lives in registers.
 struct ScanState {
@@ -832,17 +834,15 @@ int env_int(const char* name, int dflt) {
 }
 
 int plan_decode(const cvm_layout* L, int stride, int B, int K, Plan* t) {
-    const int hm = L->hm, W = L->W;
+    const int W = L->W;
     const long long HW = (long long)L->H * W;
-    // step = ring granule: one pixel per scanner thread, fewer when that could append more than kMaxAppend candidates
-    // before every warp has reached a safe point, or when the image is smaller
+    // step = ring granule: one pixel per scanner thread, fewer when the image is smaller
     int T = kScanThreads;
-    if ((long long)T * hm > kMaxAppend) T = (kMaxAppend / hm) / 32 * 32;
     if (HW < T) T = (int)((HW + 31) / 32 * 32);
     for (;; T -= 32) {
         if (T < 32) return CVM_ERR_ARG;
         t->compact_at = K + kSlack;
-        t->cap = t->compact_at + 1 + T * hm;
+        t->cap = t->compact_at + 1 + kScanThreads;   // every warp stops within 32 appends of the mark (test_hits)
         const size_t fixed = smem_bytes(0, 0, t->cap, K);
         const size_t gran_bytes = (size_t)T * stride * 4;
         if (fixed + 4 * gran_bytes > (size_t)kSmemBudget) continue;

@@ -303,119 +303,128 @@ __device__ __noinline__ void peak_pixel(const float* T, const float* Q, int hm, 
 // All shared-memory offsets become immediates, the heatmap loop is fully unrolled (HM independent element chains per
 // thread) and the rare "this pixel holds a peak" work is taken out of the hot loop.
 template <int HM, int ST_T, int ST_P>
-__global__ void __launch_bounds__(kThreads) loss_fwd_fast_kernel(const LossParams p) {
+__global__ void __launch_bounds__(kThreads + 32) loss_fwd_fast_kernel(const LossParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t full_bar[kStages];
+    __shared__ uint64_t full_bar[kStages];    // loader -> consumers: span arrived
+    __shared__ uint64_t empty_bar[kStages];   // consumers -> loader: all consumer warps are done with the stage
     __shared__ double red[kThreads / 32][CVM_NPART];
 
     float* const ring = reinterpret_cast<float*>(smem_raw);
-    const int tid = threadIdx.x;
-    constexpr int TP = kThreads;  // one pixel per thread per span
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int TP = kThreads;  // one pixel per consumer thread per span
+    constexpr int kConsumerWarps = kThreads / 32;
     constexpr size_t t_floats = (size_t)TP * ST_T;
     constexpr size_t stage_floats = (size_t)TP * (ST_T + ST_P);
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kConsumerWarps);
+        }
         mbar_fence_init();
     }
-    __syncthreads();
+    __syncthreads();   // the only CTA-wide barrier before the final reduction: loader and consumers run on their own
 
     const long long n_full = p.use_bulk ? p.n_pixels / TP : 0;  // spans below this index are full and bulk-loadable
-    auto load_span = [&](long long span, int s) {
-        float* dst_t = ring + (size_t)s * stage_floats;
-        float* dst_p = dst_t + t_floats;
-        const float* src_t = p.yt + span * (long long)(TP * ST_T);
-        const float* src_p = p.yp + span * (long long)(TP * ST_P);
-        if (span < n_full) {
-            if (tid == 0) {
-                constexpr uint32_t bt = (uint32_t)(t_floats * 4), bq = (uint32_t)((size_t)TP * ST_P * 4);
-                mbar_arrive_expect_tx(&full_bar[s], bt + bq);
-                bulk_g2s(dst_t, src_t, bt, &full_bar[s]);
-                bulk_g2s(dst_p, src_p, bq, &full_bar[s]);
+    const long long gstride = gridDim.x;
+    double v[CVM_NPART];
+#pragma unroll
+    for (int k = 0; k < CVM_NPART; ++k) v[k] = 0.0;
+
+    if (warp == kConsumerWarps) {
+        // ---- loader warp: span `it` of this CTA goes to stage it % kStages once every consumer warp has released it ----
+        int s = 0;
+        uint32_t e_parity = 0;
+        for (int it = 0;; ++it) {
+            const long long span = blockIdx.x + (long long)it * gstride;
+            if (span >= p.n_spans) break;
+            if (it >= kStages) mbar_wait(&empty_bar[s], e_parity);
+            float* dst_t = ring + (size_t)s * stage_floats;
+            float* dst_p = dst_t + t_floats;
+            const float* src_t = p.yt + span * (long long)(TP * ST_T);
+            const float* src_p = p.yp + span * (long long)(TP * ST_P);
+            if (span < n_full) {
+                if (lane == 0) {
+                    constexpr uint32_t bt = (uint32_t)(t_floats * 4), bq = (uint32_t)((size_t)TP * ST_P * 4);
+                    mbar_arrive_expect_tx(&full_bar[s], bt + bq);
+                    bulk_g2s(dst_t, src_t, bt, &full_bar[s]);
+                    bulk_g2s(dst_p, src_p, bq, &full_bar[s]);
+                }
+            } else {   // ragged last span / unaligned tensors: plain loads by the loader warp
+                const long long left = p.n_pixels - span * TP;
+                const int np = left < TP ? (int)left : TP;
+                for (int i = lane; i < np * ST_T; i += 32) dst_t[i] = src_t[i];
+                for (int i = lane; i < np * ST_P; i += 32) dst_p[i] = src_p[i];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[s]);   // release: the stores above are visible to the waiters
             }
-        } else {
+            if (++s == kStages) {
+                s = 0;
+                if (it >= kStages) e_parity ^= 1u;
+            }
+        }
+    } else {
+        // ---- consumer warps ----
+        double accN = 0.0;
+        double cold[3 + CVM_MAX_FIELDS];
+#pragma unroll
+        for (int f = 0; f < 3 + CVM_MAX_FIELDS; ++f) cold[f] = 0.0;
+        const int wch = p.wch;
+        float sN = 0.f;
+        int folded = 0, s = 0;
+        uint32_t f_parity = 0;
+        for (int it = 0;; ++it) {
+            const long long span = blockIdx.x + (long long)it * gstride;
+            if (span >= p.n_spans) break;
             const long long left = p.n_pixels - span * TP;
             const int np = left < TP ? (int)left : TP;
-            for (int i = tid; i < np * ST_T; i += kThreads) dst_t[i] = src_t[i];
-            for (int i = tid; i < np * ST_P; i += kThreads) dst_p[i] = src_p[i];
-        }
-    };
-
-    const long long gstride = gridDim.x;
-    for (int s = 0; s < kStages; ++s) {
-        const long long span = blockIdx.x + (long long)s * gstride;
-        if (span < p.n_spans) load_span(span, s);
-    }
-
-    double accN = 0.0;
-    double cold[3 + CVM_MAX_FIELDS];
+            mbar_wait(&full_bar[s], f_parity);
+            const float* __restrict__ T = ring + (size_t)s * stage_floats + tid * ST_T;
+            const float* __restrict__ Q = ring + (size_t)s * stage_floats + t_floats + tid * ST_P;
+            if (tid < np) {
+                const float w = wch >= 0 ? T[wch] : 1.0f;
+                float acc = 0.f, ymax = 0.f;
 #pragma unroll
-    for (int f = 0; f < 3 + CVM_MAX_FIELDS; ++f) cold[f] = 0.0;
-    uint32_t phase_bits = 0;
-    const int wch = p.wch;
-    float sN = 0.f;
-    int folded = 0;
-
-    for (int it = 0;; ++it) {
-        const long long span = blockIdx.x + (long long)it * gstride;
-        if (span >= p.n_spans) break;
-        const int s = it % kStages;
-        int np = TP;
-        if (span < n_full) {
-            mbar_wait(&full_bar[s], (phase_bits >> s) & 1u);
-            phase_bits ^= (1u << s);
-        } else {
-            __syncthreads();
-            const long long left = p.n_pixels - span * TP;
-            np = left < TP ? (int)left : TP;
-        }
-        const float* __restrict__ T = ring + (size_t)s * stage_floats + tid * ST_T;
-        const float* __restrict__ Q = ring + (size_t)s * stage_floats + t_floats + tid * ST_P;
-        if (tid < np) {
-            const float w = wch >= 0 ? T[wch] : 1.0f;
-            float acc = 0.f, ymax = 0.f;
-#pragma unroll
-            for (int c = 0; c < HM; ++c) {
-                const float y = T[c];
-                const float q = Q[c];
-                const float t = 1.0f - y, t2 = t * t;                                        // alpha = 2, beta = 4 only
-                const float nl = ((t2 * t2) * (q * q)) * log_one_minus(q);                  // -neg_loss, loss.py:43-48
-                acc += (y < 1.0f) ? nl : 0.0f;                                              // neg_mask, loss.py:36
-                ymax = fmaxf(ymax, y);
+                for (int c = 0; c < HM; ++c) {
+                    const float y = T[c];
+                    const float q = Q[c];
+                    const float t = 1.0f - y, t2 = t * t;                                        // alpha = 2, beta = 4 only
+                    const float nl = ((t2 * t2) * (q * q)) * log_one_minus(q);                  // -neg_loss, loss.py:43-48
+                    acc += (y < 1.0f) ? nl : 0.0f;                                              // neg_mask, loss.py:36
+                    ymax = fmaxf(ymax, y);
+                }
+                sN = fmaf(-acc, w, sN);
+                if (ymax >= 1.0f) peak_pixel(T, Q, HM, w, p, cold);  // rare: a few dozen pixels per image (re-tests == 1.0)
             }
-            sN = fmaf(-acc, w, sN);
-            if (ymax >= 1.0f) peak_pixel(T, Q, HM, w, p, cold);  // rare: a few dozen pixels per image (re-tests == 1.0)
+            if (++folded == 8) {  // short fp32 chains (<= 8*HM addends), everything above in fp64
+                accN += (double)sN;
+                sN = 0.f;
+                folded = 0;
+            }
+            __syncwarp();   // every lane is done reading the stage
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (++s == kStages) {
+                s = 0;
+                f_parity ^= 1u;
+            }
         }
-        if (++folded == 8) {  // short fp32 chains (<= 8*HM addends), everything above in fp64
-            accN += (double)sN;
-            sN = 0.f;
-            folded = 0;
+        accN += (double)sN;
+        v[0] = cold[0];
+        v[1] = accN;
+        v[2] = cold[1];
+        v[3] = cold[2];
+#pragma unroll
+        for (int f = 0; f < CVM_MAX_FIELDS; ++f) v[4 + f] = cold[3 + f];
+#pragma unroll
+        for (int k = 0; k < CVM_NPART; ++k) {
+            const double r = warp_sum(v[k]);
+            if (lane == 0) red[warp][k] = r;
         }
-        __syncthreads();  // everyone is done with stage s
-        const long long next = span + (long long)kStages * gstride;
-        if (next < p.n_spans) load_span(next, s);
-    }
-    accN += (double)sN;
-
-    double v[CVM_NPART];
-    v[0] = cold[0];
-    v[1] = accN;
-    v[2] = cold[1];
-    v[3] = cold[2];
-#pragma unroll
-    for (int f = 0; f < CVM_MAX_FIELDS; ++f) v[4 + f] = cold[3 + f];
-#pragma unroll
-    for (int k = 4 + CVM_MAX_FIELDS; k < CVM_NPART; ++k) v[k] = 0.0;
-    const int warp = tid >> 5, lane = tid & 31;
-#pragma unroll
-    for (int k = 0; k < CVM_NPART; ++k) {
-        const double r = warp_sum(v[k]);
-        if (lane == 0) red[warp][k] = r;
     }
     __syncthreads();
     if (tid < CVM_NPART) {
         double r = 0.0;
-        for (int wi = 0; wi < kThreads / 32; ++wi) r += red[wi][tid];
+        for (int wi = 0; wi < kConsumerWarps; ++wi) r += red[wi][tid];
         p.block_partials[(size_t)blockIdx.x * CVM_NPART + tid] = r;
     }
 }
@@ -427,7 +436,7 @@ int launch_loss_fast(LossParams& p, cudaStream_t st, int* grid_out) {
     const size_t smem = (size_t)kStages * kThreads * (ST_T + ST_P) * 4;
     const int grid = loss_grid(p.n_spans, smem);
     CVM_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_fast_kernel<HM, ST_T, ST_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    loss_fwd_fast_kernel<HM, ST_T, ST_P><<<grid, kThreads, smem, st>>>(p);
+    loss_fwd_fast_kernel<HM, ST_T, ST_P><<<grid, kThreads + 32, smem, st>>>(p);
     CVM_CHECK_LAUNCH("loss_fwd_fast_kernel");
     *grid_out = grid;
     return CVM_OK;
