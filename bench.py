@@ -244,12 +244,14 @@ def run_ours(args):
         if events is not None:
             events[1].record()
         ops.loss_partials(L, y_true, y_pred, True, out=partials)
-        if world > 1:
-            dist.all_reduce(partials)
-        ops.loss_finalize(L, partials, out=loss_out)
+        # the one collective of the path: 16 doubles, summed over the ranks while the decode kernel runs
+        work = dist.all_reduce(partials, async_op=True) if world > 1 else None
         if events is not None:
             events[2].record()
         out = ops.decode_topk(L, y_pred, K=TOPK)
+        if work is not None:
+            work.wait()
+        ops.loss_finalize(L, partials, out=loss_out)
         if events is not None:
             events[3].record()
         return out
@@ -298,10 +300,11 @@ def run_ours(args):
         ops.render_gt(L, o_d, of_d, B, i_d, if_d, out=y_true)
         y_pred_in.copy_(y_pred_h, non_blocking=True)
         ops.loss_partials(L, y_true, y_pred_in, True, out=partials)
-        if world > 1:
-            dist.all_reduce(partials)
-        ops.loss_finalize(L, partials, out=loss_out)
+        work = dist.all_reduce(partials, async_op=True) if world > 1 else None
         o = ops.decode_topk(L, y_pred_in, K=TOPK)
+        if work is not None:
+            work.wait()
+        ops.loss_finalize(L, partials, out=loss_out)
         loss_h.copy_(loss_out, non_blocking=True)
         for k_, v in res_h.items():
             v.copy_(o[k_], non_blocking=True)
@@ -351,7 +354,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "CenterNet 2D-OD full heatmap path (render+loss+decode), 10-class 128x384, 32 obj/img, top-K=100 (BASELINE configs[1])",
-                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world} (batch shards, one 128-byte all-reduce)",
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world} (batch shards, one 128-byte all-reduce overlapped with decode)",
                    "l2": "inputs larger than L2 (y_pred 705 MB + y_true 755 MB per GPU per step)"},
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": load_traffic(names[dom]), "peak_source": peak_src,

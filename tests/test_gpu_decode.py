@@ -122,6 +122,40 @@ def test_topk_properties_full_size(cuda):
     _check_topk({k: v[:3] for k, v in out.items() if v is not None}, ref, 100)
 
 
+def test_topk_multitask_wide_map(cuda):
+    """BASELINE configs[4] layout: CenterNet channels [0:14] inside a 20-channel multitask tensor, W = 1536 (the 3x3
+    neighbours of a pixel are too far apart to stay in the shared-memory ring: they are read from global memory), plus
+    the semseg argmax of channels [14:19] of the same tensor."""
+    from cvmhot import ops
+    from cvmhot.layout import layout_from_params
+    from cvmhot.common.utils.image import class_ids
+    from oracle import image_np
+    H, W, C, B = 24, 1536, 10, 3
+    Lo = make_layout(H, W, C, "N")
+    data = synth.make_batch(Lo, 9, B)
+    rng = np.random.default_rng(3)
+    wide = rng.normal(0, 1, (B, H, W, 20)).astype(np.float32)
+    wide[..., :Lo.Cp] = data["y_pred"]
+    ref = decode_np.decode_topk(Lo, data["y_pred"], 100)
+    wide_d = torch.from_numpy(wide).to(cuda)
+    out = ops.decode_topk(layout_from_params(_params(C, True, H, W)), wide_d[..., :Lo.Cp], K=100)
+    _check_topk(out, ref, 100)
+    ids = class_ids(wide_d, 14, 5).cpu().numpy()
+    assert np.array_equal(ids, image_np.class_ids(wide[..., 14:19], 5))
+
+
+@pytest.mark.parametrize("H,W,K_cls,B", [(40, 64, 40, 2), (33, 35, 3, 3)])
+def test_topk_many_classes_and_unaligned(cuda, H, W, K_cls, B):
+    """hm > 32 exercises the 64-bit channel masks; H*W*Cp not a multiple of 4 floats disables the bulk-copy engine (the
+    loader warp copies with plain loads)."""
+    from cvmhot.models.centernet.post_processing import decode_topk
+    Lo = make_layout(H, W, K_cls, "N")
+    data = synth.make_batch(Lo, 11, B)
+    ref = decode_np.decode_topk(Lo, data["y_pred"], 100)
+    out = decode_topk(torch.from_numpy(data["y_pred"]).to(cuda), _params(K_cls, True, H, W), K=100)
+    _check_topk(out, ref, ref["scores"].shape[1])
+
+
 def test_window9_vs_real_golden(cuda, golden_dir):
     from cvmhot.models.centernet import CenternetParams, process_2d_output
     from cvmhot.common.utils import Roi
