@@ -34,7 +34,7 @@ constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kThreads = kScanThreads + 32;   // + the loader warp
 constexpr int kMergeThreads = 256;
 constexpr int kMaxSlots = 32;      // ring depth (granules) the barrier arrays can hold
-constexpr int kSlack = 2048;       // buffer entries beyond K before the (rare) fallback compaction
+constexpr int kSlack = 1536;       // buffer entries beyond K before the (rare) fallback compaction
 constexpr int kSegKeys = 512;      // keys a segment may publish without an exact select (the merge kernel selects anyway)
 constexpr int kScoreShift = 19;    // score histogram: bin = float bits >> 19 (sign 0, 8 exponent bits, 4 mantissa bits)
 constexpr int kScoreBins = 1 << (31 - kScoreShift);
@@ -46,8 +46,9 @@ struct DecodeParams {
     const float* yp;
     int stride, H, W, hm, K;
     int HW;                       // pixels per image
-    int T;                        // pixels per step = pixels per ring granule (<= kScanThreads)
-    int spi;                      // steps (= granules) per image
+    int T;                        // pixels per ring granule (<= kScanThreads)
+    int gps;                      // granules per step (pixels per scanner lane and step)
+    int spi, gpi;                 // steps / granules per image
     long long n_steps;            // B * spi
     int S;                        // ring slots (granules)
     int ring_nb;                  // 1: neighbours are read from the ring; 0: from global memory
@@ -313,12 +314,84 @@ struct Hit {
     int rp;                    // ring position (in pixels) of the pixel
 };
 
-// Exact 3x3 test of the pending hits of a warp and append of the peaks.  Called by ALL lanes of the warp (lanes without
-// a hit pass mask 0): the loop runs over the union of the lanes' channel masks, so votes and the aggregated append (one
-// shared atomic per warp and channel) are warp-uniform.  img: image of the pixels.
-__device__ __forceinline__ void test_hits(const DecodeParams& p, long long img, const Hit& hit, float thr_f) {
-    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)hit.mask);
-    const unsigned hi = p.hm > 32 ? __reduce_or_sync(0xffffffffu, (unsigned)(hit.mask >> 32)) : 0u;
+// Offsets (in floats) of channel 0 of the eight neighbours of a hit pixel: into the ring (W + 1 pixels of halo are
+// resident) or relative to the pixel in global memory; INT_MIN outside the map.  Interior pixels whose neighbourhood does
+// not wrap around the ring (almost all) take the short way.
+__device__ __forceinline__ void neighbour_offsets(const DecodeParams& p, const Hit& hit, int (&nb)[8]) {
+    const int W = p.W, stride = p.stride, ring_px = p.S * p.T;
+    // y = q / W without an integer division (exact after one correction step for any q < 2^31)
+    const int q = hit.q;
+    int y = __float2int_rz(__fmul_rn((float)q, p.inv_W)), x = q - y * W;
+    if (x < 0) {
+        --y;
+        x += W;
+    } else if (x >= W) {
+        ++y;
+        x -= W;
+    }
+    const bool interior = y > 0 && y < p.H - 1 && x > 0 && x < W - 1;
+    const bool flat = !p.ring_nb || (hit.rp - W - 1 >= 0 && hit.rp + W + 1 < ring_px);
+    if (interior && flat) {
+        const int base = p.ring_nb ? hit.rp * stride : 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int j = k < 4 ? k : k + 1;
+            nb[k] = base + ((j / 3 - 1) * W + (j % 3 - 1)) * stride;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int j = k < 4 ? k : k + 1;
+            const int dy = j / 3 - 1, dx = j % 3 - 1;
+            const int yy = y + dy, xx = x + dx;
+            int off = INT_MIN;
+            if (yy >= 0 && yy < p.H && xx >= 0 && xx < W) {
+                const int dq = dy * W + dx;
+                if (p.ring_nb) {
+                    int r = hit.rp + dq;
+                    if (r < 0) r += ring_px;
+                    if (r >= ring_px) r -= ring_px;
+                    off = r * stride;
+                } else {
+                    off = dq * stride;
+                }
+            }
+            nb[k] = off;
+        }
+    }
+}
+
+// is channel ch of the hit pixel a peak (its value equals its 3x3 maximum; plateaus are all kept) that still reaches the
+// threshold (it may have risen since the scan; it is > 0, so score-0 entries never get here)?
+__device__ __forceinline__ bool is_peak(const DecodeParams& p, const float* ring, const float* g_px, const Hit& hit,
+                                        const int (&nb)[8], int ch, float thr_f, float& v) {
+    if (!((hit.mask >> ch) & 1ull)) return false;
+    v = ring[hit.rp * p.stride + ch];
+    if (!(v >= thr_f)) return false;
+    float m = v;
+    if (p.ring_nb) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (nb[k] != INT_MIN) m = fmaxf(m, ring[nb[k] + ch]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (nb[k] != INT_MIN) m = fmaxf(m, g_px[nb[k] + ch]);
+    }
+    return m == v;
+}
+
+// Exact 3x3 test of the pending hits of a warp (NH pixels per lane) and append of the peaks.  Called by ALL lanes of the
+// warp (lanes without a hit pass mask 0): the loop runs over the union of the lanes' channel masks, so votes and the
+// aggregated append (one shared atomic per warp and channel) are warp-uniform; the NH pixels of a lane are tested side
+// by side (independent load chains).  img: image of the pixels.
+template <int NH>
+__device__ __forceinline__ void test_hits(const DecodeParams& p, long long img, const Hit (&hit)[NH], float thr_f) {
+    unsigned long long any = 0ull;
+#pragma unroll
+    for (int k = 0; k < NH; ++k) any |= hit[k].mask;
+    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)any);
+    const unsigned hi = p.hm > 32 ? __reduce_or_sync(0xffffffffu, (unsigned)(any >> 32)) : 0u;
     unsigned long long uni = ((unsigned long long)hi << 32) | lo;
     if (uni == 0ull) return;
     SharedHead* h = sm_head();
@@ -326,94 +399,49 @@ __device__ __forceinline__ void test_hits(const DecodeParams& p, long long img, 
     unsigned long long* cand = sm_cand(p);
     unsigned int* shist = sm_shist(p);
     const int lane = threadIdx.x & 31;
-    const int W = p.W, stride = p.stride, ring_px = p.S * p.T;
-    // channel 0 of the eight neighbours as an offset (in floats) into the ring (W + 1 pixels of halo are resident) or
-    // relative to this pixel in global memory; INT_MIN outside the map.  Interior pixels whose neighbourhood does not
-    // wrap around the ring (almost all) take the short way.
-    int nb[8];
-    const float* g_px = p.yp;
-    if (hit.mask) {
-        // y = q / W without an integer division (exact after one correction step for any q < 2^31)
-        const int q = hit.q;
-        int y = __float2int_rz(__fmul_rn((float)q, p.inv_W)), x = q - y * W;
-        if (x < 0) {
-            --y;
-            x += W;
-        } else if (x >= W) {
-            ++y;
-            x -= W;
-        }
-        g_px += ((size_t)img * p.HW + (size_t)q) * stride;
-        const bool interior = y > 0 && y < p.H - 1 && x > 0 && x < W - 1;
-        const bool flat = !p.ring_nb || (hit.rp - W - 1 >= 0 && hit.rp + W + 1 < ring_px);
-        if (interior && flat) {
-            const int base = p.ring_nb ? hit.rp * stride : 0;
+    int nb[NH][8];
+    const float* g_px[NH];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int j = k < 4 ? k : k + 1;
-                nb[k] = base + ((j / 3 - 1) * W + (j % 3 - 1)) * stride;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int j = k < 4 ? k : k + 1;
-                const int dy = j / 3 - 1, dx = j % 3 - 1;
-                const int yy = y + dy, xx = x + dx;
-                int off = INT_MIN;
-                if (yy >= 0 && yy < p.H && xx >= 0 && xx < W) {
-                    const int dq = dy * W + dx;
-                    if (p.ring_nb) {
-                        int r = hit.rp + dq;
-                        if (r < 0) r += ring_px;
-                        if (r >= ring_px) r -= ring_px;
-                        off = r * stride;
-                    } else {
-                        off = dq * stride;
-                    }
-                }
-                nb[k] = off;
-            }
-        }
+    for (int k = 0; k < NH; ++k) {
+        g_px[k] = p.yp + ((size_t)img * p.HW + (size_t)hit[k].q) * p.stride;
+        if (hit[k].mask) neighbour_offsets(p, hit[k], nb[k]);
     }
     while (uni) {
         const int ch = __ffsll((long long)uni) - 1;
         uni &= uni - 1;
-        bool peak = false;
-        float v = 0.f;
-        if ((hit.mask >> ch) & 1ull) {
-            v = ring[hit.rp * stride + ch];
-            if (v >= thr_f) {   // the threshold may have risen since the scan; it is > 0, so score-0 entries never get here
-                float m = v;
-                if (p.ring_nb) {
+        bool peak[NH];
+        float v[NH];
+        unsigned pm[NH], total = 0;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (nb[k] != INT_MIN) m = fmaxf(m, ring[nb[k] + ch]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (nb[k] != INT_MIN) m = fmaxf(m, g_px[nb[k] + ch]);
-                }
-                peak = m == v;   // the value equals its 3x3 maximum (plateaus are all kept)
-            }
+        for (int k = 0; k < NH; ++k) {
+            v[k] = 0.f;
+            peak[k] = is_peak(p, ring, g_px[k], hit[k], nb[k], ch, thr_f, v[k]);
         }
-        const unsigned pm = __ballot_sync(0xffffffffu, peak);
-        if (pm) {
-            const int leader = __ffs(pm) - 1;
+#pragma unroll
+        for (int k = 0; k < NH; ++k) {
+            pm[k] = __ballot_sync(0xffffffffu, peak[k]);
+            total += __popc(pm[k]);
+        }
+        if (total) {
             unsigned base = 0;
-            if (lane == leader) base = (unsigned)atomicAdd(&h->count, __popc(pm));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (peak) {
-                const unsigned pos = base + __popc(pm & ((1u << lane) - 1u));
-                const unsigned bits = __float_as_uint(v);
-                const unsigned flat = (unsigned)hit.q * (unsigned)p.hm + (unsigned)ch;
-                cand[pos] = ((unsigned long long)bits << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
-                if (pos >= (unsigned)p.compact_at) *(volatile int*)&h->compact_flag = 1;
-                const unsigned bin = bits >> kScoreShift;
-                atomicAdd(&shist[bin], 1u);
-                if ((int)bin > *(volatile int*)&h->maxbin) atomicMax(&h->maxbin, (int)bin);
+            if (lane == 0) base = (unsigned)atomicAdd(&h->count, (int)total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+            for (int k = 0; k < NH; ++k) {
+                if (peak[k]) {
+                    const unsigned pos = base + __popc(pm[k] & ((1u << lane) - 1u));
+                    const unsigned bits = __float_as_uint(v[k]);
+                    const unsigned flat = (unsigned)hit[k].q * (unsigned)p.hm + (unsigned)ch;
+                    cand[pos] = ((unsigned long long)bits << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
+                    if (pos >= (unsigned)p.compact_at) *(volatile int*)&h->compact_flag = 1;
+                    const unsigned bin = bits >> kScoreShift;
+                    atomicAdd(&shist[bin], 1u);
+                    if ((int)bin > *(volatile int*)&h->maxbin) atomicMax(&h->maxbin, (int)bin);
+                }
+                base += __popc(pm[k]);
             }
             // Safe point after every batch of appends: once the buffer has passed its mark, a warp adds at most these
-            // <= 32 keys before it joins the compaction, which bounds the buffer (cap = mark + 32 per scanner warp).
+            // <= 32 * NH keys before it joins the compaction, which bounds the buffer (see plan_decode).
             __syncwarp();
             if (__any_sync(0xffffffffu, load_ctrl(h).y != 0)) gather(p, false, 0);
         }
@@ -532,26 +560,28 @@ __device__ __forceinline__ void release_until(const DecodeParams& p, ScanState& 
     }
 }
 
-// STRIDE/HM = 0: runtime pixel stride / heatmap channel count.  BULK: granules arrive by bulk async copy (needs 16-byte
-// aligned granules); otherwise the loader warp copies them with plain loads.
-template <int STRIDE, int HM, bool BULK>
+// STRIDE/HM = 0: runtime pixel stride / heatmap channel count.  GPS: granules (= pixels per lane) per step.  BULK: granules
+// arrive by bulk async copy (needs 16-byte aligned granules); otherwise the loader warp copies them with plain loads.
+template <int STRIDE, int HM, int GPS, bool BULK>
 __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_constant__ DecodeParams p) {
     SharedHead* const h = sm_head();
     float* const ring = sm_ring();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int S = p.S, T = p.T, spi = p.spi, HW = p.HW, hg = p.halo_g;
+    const int S = p.S, T = p.T, spi = p.spi, gpi = p.gpi, HW = p.HW, hg = p.halo_g;
     const int stride = STRIDE ? STRIDE : p.stride;
 
-    // this CTA's contiguous range of the flat step list; granule `seq` of the CTA is flat step s0 - lead + seq
+    // this CTA's contiguous range of the flat step list (a step = GPS consecutive granules of one image); granule `seq`
+    // of the CTA is flat granule g_first + seq (every image has gpi granules, so flat granule indices are contiguous)
     const long long G = gridDim.x, g = blockIdx.x;
     const long long s0 = g * p.n_steps / G, s1 = (g + 1) * p.n_steps / G;
     if (s0 >= s1) return;
     const long long img0 = s0 / spi, imgL = (s1 - 1) / spi;
     const int st0 = (int)(s0 - img0 * spi), stL = (int)((s1 - 1) - imgL * spi);
     const int n_local = (int)(s1 - s0);
-    const int lead = min(hg, st0);              // history granules before the first step (same image only)
-    const int tail = min(hg, spi - 1 - stL);    // lookahead granules after the last step (same image only)
-    const int n_load = lead + n_local + tail;
+    const int lead = min(hg, st0 * GPS);                       // history granules before the first step (same image only)
+    const int endL = min(gpi, (stL + 1) * GPS);                // first granule after the last step
+    const int tail = min(hg, gpi - endL);                      // lookahead granules after the last step (same image only)
+    const int n_load = (int)((imgL - img0) * gpi + endL + tail - (st0 * GPS - lead));
 
     if (tid == 0) {
         for (int k = 0; k < S; ++k) {
@@ -572,7 +602,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
 
     if (warp == kScanWarps) {
         // ---- loader warp: granule `seq` goes to slot seq % S once all scanner warps have released its previous tenant ----
-        int slot = 0, gi = st0 - lead;
+        int slot = 0, gi = st0 * GPS - lead;
         long long l_img = img0;
         uint32_t e_parity = 0;   // parity of the empty-barrier phase that frees a slot for its next tenant
         for (int seq = 0; seq < n_load; ++seq) {
@@ -581,8 +611,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
                 long long spins = 0;
                 while (!mbar_try_wait(&h->empty_bar[slot], e_parity)) {
                     if (++spins > 16000000LL) {
-                        if (lane == 0)
-                        {
+                        if (lane == 0) {
                             printf("loader stuck: cta %d seq %d n_load %d slot %d flag %d seg_done %d count %d\n", (int)blockIdx.x, seq,
                                    n_load, slot, h->compact_flag, h->seg_done, h->count);
                             volatile int* d = h->dbg_state;
@@ -615,7 +644,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
                 slot = 0;
                 if (seq >= S) e_parity ^= 1u;
             }
-            if (++gi == spi) {
+            if (++gi == gpi) {
                 gi = 0;
                 ++l_img;
             }
@@ -631,34 +660,43 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
 
     long long img = img0;
     int st = st0;
-    int cur_slot = lead;     // slot of the current step's granule (lead <= halo_g < S)
-    Hit prev;                // this lane's pixel of the previous step, if it reached the threshold: waits for its 3x3 test
-    prev.mask = 0ull;
-    prev.q = prev.rp = 0;
+    int gseq = lead;         // sequence number of the first granule of the current step
+    int cur_slot = lead;     // its ring slot (lead <= halo_g < S)
+    Hit prev[GPS];           // this lane's pixels of the previous step that reached the threshold: wait for their 3x3 test
+#pragma unroll
+    for (int k = 0; k < GPS; ++k) {
+        prev[k].mask = 0ull;
+        prev[k].q = prev[k].rp = 0;
+    }
 
     for (int i = 0; i < n_local; ++i) {
-        const int seq = i + lead;
-        const int q0 = st * T, npx = min(T, HW - q0);
+        const int g0 = st * GPS;                                 // first granule of the step inside the image
+        const int gc = min(GPS, gpi - g0);                        // granules in this step (the last step of an image may be short)
         // last granule of this image that this CTA fetches
-        const int seq_last = min(seq + (spi - 1 - st), n_load - 1);
-        // this step's granule, and the lookahead of the previous step's pixels (W + 1 pixels past its end)
+        const int seq_last = min(gseq + (gpi - 1 - g0), n_load - 1);
+        // this step's granules, and the lookahead of the previous step's pixels (W + 1 pixels past its end)
         DBG_STATE(100 + i * 1000);
-        wait_until(p, z, min(max(seq, seq - 1 + hg), seq_last) + 1);
+        wait_until(p, z, min(max(gseq + gc - 1, gseq - 1 + hg), seq_last) + 1);
         DBG_STATE(101 + i * 1000);
-        test_hits(p, img, prev, z.thr_f);
+        test_hits<GPS>(p, img, prev, z.thr_f);
         // this step: one compare per pixel
         DBG_STATE(102 + i * 1000);
-        const int rp = cur_slot * T + tid;   // ring position of this lane's pixel
-        Hit cur;
-        cur.mask = 0ull;
-        cur.q = q0 + tid;
-        cur.rp = rp;
-        if (tid < npx) {
-            const float* px = ring + (size_t)rp * stride;
-            if (pixel_max<STRIDE, HM>(px, p.hm) >= z.thr_f) cur.mask = channel_mask<HM>(px, p.hm, z.thr_f);
+        Hit cur[GPS];
+#pragma unroll
+        for (int k = 0; k < GPS; ++k) {
+            int sl = cur_slot + k;
+            if (sl >= S) sl -= S;
+            const int q0 = (g0 + k) * T;
+            cur[k].mask = 0ull;
+            cur[k].q = q0 + tid;
+            cur[k].rp = sl * T + tid;   // ring position of this lane's pixel
+            if (k < gc && tid < min(T, HW - q0)) {
+                const float* px = ring + (size_t)cur[k].rp * stride;
+                if (pixel_max<STRIDE, HM>(px, p.hm) >= z.thr_f) cur[k].mask = channel_mask<HM>(px, p.hm, z.thr_f);
+            }
         }
         // the next step tests this step's pixels and needs halo_g granules of history before it: the rest is dead
-        release_until(p, z, seq - hg);
+        release_until(p, z, gseq - hg);
         __syncwarp();   // converged: the control word below is one broadcast load, the same pair for all lanes
         const uint2 ctrl = load_ctrl(h);
         z.thr_f = __uint_as_float(ctrl.x);   // stale values are still valid bounds
@@ -670,24 +708,28 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
                 gather(p, false, 0);
                 z.thr_f = __uint_as_float(load_ctrl(h).x);
             }
-            prev = cur;
+#pragma unroll
+            for (int k = 0; k < GPS; ++k) prev[k] = cur[k];
             ++st;
         } else {
             // drain: test this step's hits now (the lookahead, if any, belongs to the next CTA's range and was fetched too)
-            wait_until(p, z, min(seq + hg, seq_last) + 1);
-            test_hits(p, img, cur, z.thr_f);
+            wait_until(p, z, min(gseq + gc - 1 + hg, seq_last) + 1);
+            test_hits<GPS>(p, img, cur, z.thr_f);
             const bool image_end = st + 1 == spi;
-            release_until(p, z, image_end ? seq + 1 : n_load);   // the rest of the image / of the range is dead
+            release_until(p, z, image_end ? gseq + gc : n_load);   // the rest of the image / of the range is dead
             if (lane == 0) atomicAdd(&h->seg_done, 1);
             gather(p, true, (int)(img - img0));
             z.thr_f = __uint_as_float(p.thr0_bits);
-            prev.mask = 0ull;
+#pragma unroll
+            for (int k = 0; k < GPS; ++k) prev[k].mask = 0ull;
             if (image_end) {
                 st = 0;
                 ++img;
             }
         }
-        if (++cur_slot == S) cur_slot = 0;
+        gseq += gc;
+        cur_slot += gc;
+        if (cur_slot >= S) cur_slot -= S;
     }
 }
 
@@ -823,7 +865,7 @@ __global__ void __launch_bounds__(kMergeThreads) decode_merge_kernel(const Merge
 
 
 struct Plan {
-    int T, spi, S, ring_nb, halo_g, gran_floats, cap, compact_at, grid, max_segs, seg_keys;
+    int T, gps, spi, gpi, S, ring_nb, halo_g, gran_floats, cap, compact_at, grid, max_segs, seg_keys;
     long long n_steps;
     size_t smem_scan, smem_merge, ws_keys, ws_total;
 };
@@ -836,39 +878,51 @@ int env_int(const char* name, int dflt) {
 int plan_decode(const cvm_layout* L, int stride, int B, int K, Plan* t) {
     const int W = L->W;
     const long long HW = (long long)L->H * W;
-    // step = ring granule: one pixel per scanner thread, fewer when the image is smaller
+    // granule: one pixel per scanner thread, fewer when the image is smaller; a step is 2 granules when the ring has room
+    // (the per-step bookkeeping and the latency of the hit tests are then paid once per 2 pixels of every lane)
     int T = kScanThreads;
     if (HW < T) T = (int)((HW + 31) / 32 * 32);
+    t->compact_at = K + kSlack;
+    t->cap = t->compact_at + 1 + 2 * kScanThreads;   // every warp stops within 32 appends per pixel of a lane of the mark (test_hits)
+    const size_t fixed = smem_bytes(0, 0, t->cap, K);
+    int gps_want = env_int("CVM_DECODE_GPS", 2);
+    if (gps_want < 1 || gps_want > 2 || HW <= T) gps_want = 1;
     for (;; T -= 32) {
         if (T < 32) return CVM_ERR_ARG;
-        t->compact_at = K + kSlack;
-        t->cap = t->compact_at + 1 + kScanThreads;   // every warp stops within 32 appends of the mark (test_hits)
-        const size_t fixed = smem_bytes(0, 0, t->cap, K);
         const size_t gran_bytes = (size_t)T * stride * 4;
         if (fixed + 4 * gran_bytes > (size_t)kSmemBudget) continue;
         int S = (int)(((size_t)kSmemBudget - fixed) / gran_bytes);
         if (S > kMaxSlots) S = kMaxSlots;
-        // ring mode keeps 2 * halo_g + 1 granules resident (history and lookahead of the tested step), global-neighbour
-        // mode keeps 2; both want at least two more in flight
+        // ring mode keeps halo_g + gps + max(gps, halo_g) granules resident (history, the tested step, the scanned step /
+        // the lookahead of the tested one); global-neighbour mode keeps 2 * gps; both want two more in flight
         const int hg = (W + 1 + T - 1) / T;
-        if (S >= 2 * hg + 3) {
-            t->ring_nb = 1;
-            t->halo_g = hg;
-            t->S = S < 2 * hg + 5 ? S : 2 * hg + 5;
-        } else {
+        t->gps = 0;
+        for (int gps = gps_want; gps >= 1 && !t->gps; --gps) {
+            const int need = hg + gps + (gps > hg ? gps : hg) + 2;
+            if (S >= need) {
+                t->gps = gps;
+                t->ring_nb = 1;
+                t->halo_g = hg;
+                t->S = need;
+            }
+        }
+        if (!t->gps) {
+            t->gps = S >= 6 ? gps_want : 1;
             t->ring_nb = 0;
             t->halo_g = 0;
-            t->S = S < 6 ? S : 6;
+            t->S = S < 2 * t->gps + 2 ? S : 2 * t->gps + 2;
         }
         t->gran_floats = T * stride;
         break;
     }
     {
         const int v = env_int("CVM_DECODE_S", 0);   // experiment knob: ring depth
-        if (v >= 2 * t->halo_g + 3 && v <= kMaxSlots && smem_bytes(v, t->gran_floats, t->cap, K) <= (size_t)kSmemBudget) t->S = v;
+        const int need = t->ring_nb ? t->halo_g + t->gps + (t->gps > t->halo_g ? t->gps : t->halo_g) + 1 : 2 * t->gps;
+        if (v >= need && v <= kMaxSlots && smem_bytes(v, t->gran_floats, t->cap, K) <= (size_t)kSmemBudget) t->S = v;
     }
     t->T = T;
-    t->spi = (int)((HW + T - 1) / T);
+    t->gpi = (int)((HW + T - 1) / T);
+    t->spi = (t->gpi + t->gps - 1) / t->gps;
     t->n_steps = (long long)B * t->spi;
     long long grid = cvm_num_sms();
     if (grid > t->n_steps) grid = t->n_steps;
@@ -894,19 +948,19 @@ int check_decode_args(const cvm_layout* L, int stride, int B, int K) {
     return CVM_OK;
 }
 
-template <int STRIDE, int HM>
-int launch_scan(const DecodeParams& p, const Plan& t, bool bulk, cudaStream_t st) {
-    if (bulk) {
-        CVM_CHECK_CUDA(cudaFuncSetAttribute(decode_scan_kernel<STRIDE, HM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)t.smem_scan));
-        decode_scan_kernel<STRIDE, HM, true><<<t.grid, kThreads, t.smem_scan, st>>>(p);
-    } else {
-        CVM_CHECK_CUDA(cudaFuncSetAttribute(decode_scan_kernel<STRIDE, HM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)t.smem_scan));
-        decode_scan_kernel<STRIDE, HM, false><<<t.grid, kThreads, t.smem_scan, st>>>(p);
-    }
+template <int STRIDE, int HM, int GPS, bool BULK>
+int launch_scan_one(const DecodeParams& p, const Plan& t, cudaStream_t st) {
+    CVM_CHECK_CUDA(cudaFuncSetAttribute(decode_scan_kernel<STRIDE, HM, GPS, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)t.smem_scan));
+    decode_scan_kernel<STRIDE, HM, GPS, BULK><<<t.grid, kThreads, t.smem_scan, st>>>(p);
     CVM_CHECK_LAUNCH("decode_scan_kernel");
     return CVM_OK;
+}
+
+template <int STRIDE, int HM>
+int launch_scan(const DecodeParams& p, const Plan& t, bool bulk, cudaStream_t st) {
+    if (t.gps == 2) return bulk ? launch_scan_one<STRIDE, HM, 2, true>(p, t, st) : launch_scan_one<STRIDE, HM, 2, false>(p, t, st);
+    return bulk ? launch_scan_one<STRIDE, HM, 1, true>(p, t, st) : launch_scan_one<STRIDE, HM, 1, false>(p, t, st);
 }
 
 }  // namespace
@@ -943,7 +997,9 @@ extern "C" int cvm_decode_topk(const cvm_layout* L, const float* y_pred, int pre
     p.K = K;
     p.HW = L->H * L->W;
     p.T = t.T;
+    p.gps = t.gps;
     p.spi = t.spi;
+    p.gpi = t.gpi;
     p.n_steps = t.n_steps;
     p.S = t.S;
     p.ring_nb = t.ring_nb;
