@@ -299,6 +299,25 @@ __device__ __noinline__ void peak_pixel(const float* T, const float* Q, int hm, 
     cold[0] += (double)sP;
 }
 
+// ---- packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2, PTX *.f32x2): two lanes per instruction, IEEE rounding per lane ----
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk2(float a, float b) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpk2(f2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // ---- fast path: channel counts known at compile time, one pixel per thread ------------------------------------------
 // All shared-memory offsets become immediates, the heatmap loop is fully unrolled (HM independent element chains per
 // thread) and the rare "this pixel holds a peak" work is taken out of the hot loop.
@@ -383,17 +402,65 @@ __global__ void __launch_bounds__(kThreads + 32) loss_fwd_fast_kernel(const Loss
             const float* __restrict__ Q = ring + (size_t)s * stage_floats + t_floats + tid * ST_P;
             if (tid < np) {
                 const float w = wch >= 0 ? T[wch] : 1.0f;
-                float acc = 0.f, ymax = 0.f;
+                float ymax = 0.f;
+                // Two heatmap channels per instruction: sm_100's packed fp32 pipe (FFMA2/FMUL2, PTX *.f32x2) runs the
+                // multiplies and the log1p series of a channel pair in one issue slot each; per lane the operations and
+                // their rounding are those of the scalar code (the kernel is issue bound, not HBM bound).  acc2 holds
+                // +neg_loss of the even / odd channels.  For y <= 1 the neg_mask (loss.py:36) is implied by (1-y)^4 = 0
+                // at y == 1; a pixel with some y > 1 (never produced by the render) is redone exactly below.
+                f2 acc2 = pk2(0.f, 0.f);
 #pragma unroll
-                for (int c = 0; c < HM; ++c) {
-                    const float y = T[c];
-                    const float q = Q[c];
-                    const float t = 1.0f - y, t2 = t * t;                                        // alpha = 2, beta = 4 only
-                    const float nl = ((t2 * t2) * (q * q)) * log_one_minus(q);                  // -neg_loss, loss.py:43-48
-                    acc += (y < 1.0f) ? nl : 0.0f;                                              // neg_mask, loss.py:36
+                for (int c = 0; c + 1 < HM; c += 2) {
+                    const float y0 = T[c], y1 = T[c + 1];
+                    float q0, q1;
+                    f2 q;
+                    if (ST_P % 2 == 0) {
+                        q = *reinterpret_cast<const f2*>(Q + c);   // 8-byte aligned: even pixel stride, even channel
+                        unpk2(q, q0, q1);
+                    } else {
+                        q0 = Q[c];
+                        q1 = Q[c + 1];
+                        q = pk2(q0, q1);
+                    }
+                    const f2 t = fma2(pk2(y0, y1), pk2(-1.f, -1.f), pk2(1.f, 1.f));               // 1 - y
+                    const f2 t2 = mul2(t, t);                                                      // alpha = 2, beta = 4 only
+                    const f2 tq = mul2(mul2(t2, t2), mul2(q, q));
+                    // -log(clip(1 - q, .01, .99)) (loss.py:47), see log_one_minus(): series below 1/16, MUFU.LG2 above
+                    const float z0 = fminf(fmaxf(q0, 0.01f), 0.99f), z1 = fminf(fmaxf(q1, 0.01f), 0.99f);
+                    const f2 z = pk2(z0, z1);
+                    f2 sr = fma2(z, pk2(1.0f / 6.0f, 1.0f / 6.0f), pk2(0.2f, 0.2f));
+                    sr = fma2(z, sr, pk2(0.25f, 0.25f));
+                    sr = fma2(z, sr, pk2(1.0f / 3.0f, 1.0f / 3.0f));
+                    sr = fma2(z, sr, pk2(0.5f, 0.5f));
+                    sr = fma2(z, sr, pk2(1.0f, 1.0f));
+                    float s0, s1;
+                    unpk2(mul2(z, sr), s0, s1);                                                    // -log1p(-z) for small z
+                    float lg0, lg1;
+                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg0) : "f"(1.0f - z0));
+                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg1) : "f"(1.0f - z1));
+                    const float l0 = z0 < 0.0625f ? s0 : lg0 * -0.69314718055994530942f;
+                    const float l1 = z1 < 0.0625f ? s1 : lg1 * -0.69314718055994530942f;
+                    acc2 = fma2(tq, pk2(l0, l1), acc2);                                            // +neg_loss, loss.py:43-48
+                    ymax = fmaxf(ymax, fmaxf(y0, y1));
+                }
+                float a0, a1;
+                unpk2(acc2, a0, a1);
+                float acc = a0 + a1;
+                if (HM & 1) {   // odd channel count: the last channel on the scalar path
+                    const float y = T[HM - 1], q = Q[HM - 1];
+                    const float t = 1.0f - y, t2 = t * t;
+                    acc -= ((t2 * t2) * (q * q)) * log_one_minus(q);
                     ymax = fmaxf(ymax, y);
                 }
-                sN = fmaf(-acc, w, sN);
+                if (ymax > 1.0f) {   // out-of-range targets: the masked sum, channel by channel
+                    acc = 0.f;
+                    for (int c = 0; c < HM; ++c) {
+                        const float y = T[c], q = Q[c];
+                        const float t = 1.0f - y, t2 = t * t;
+                        if (y < 1.0f) acc -= ((t2 * t2) * (q * q)) * log_one_minus(q);
+                    }
+                }
+                sN = fmaf(acc, w, sN);
                 if (ymax >= 1.0f) peak_pixel(T, Q, HM, w, p, cold);  // rare: a few dozen pixels per image (re-tests == 1.0)
             }
             if (++folded == 8) {  // short fp32 chains (<= 8*HM addends), everything above in fp64
