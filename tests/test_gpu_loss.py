@@ -180,3 +180,52 @@ def test_backward_vs_autograd(cuda, profile, track, allf):
     g, gr = yp_d.grad.cpu().double(), yp64.grad
     scale = gr.abs().max()
     assert torch.allclose(g, gr, rtol=1e-4, atol=float(scale) * 1e-6)
+
+
+def test_loss_properties_full_size(cuda):
+    """BASELINE configs[1] shape (B sampled down to 32): the partials vector is additive over batch shards (this is what the
+    multi-GPU all-reduce relies on), bit-reproducible run to run, and the total agrees with the fp64 oracle."""
+    import bench
+    from cvmhot import ops
+    from cvmhot.layout import layout_from_params
+    from cvmhot.models.centernet import CenternetParams
+    H, W, K, B = 128, 384, 10, 32
+    p = CenternetParams(K, True)
+    p.INPUT_HEIGHT, p.INPUT_WIDTH = H * p.R, W * p.R
+    L = layout_from_params(p)
+    Lo = make_layout(H, W, K, "N")
+    boxes, cls, ign = bench.gen_objects(0, B)
+    yt = np.stack([render_np.render_image(Lo, boxes[b], cls[b], ign[b]) for b in range(B)])
+    rng = np.random.default_rng(21)
+    yp = np.zeros((B, H, W, Lo.Cp), np.float32)
+    yp[..., :K] = 1.0 / (1.0 + np.exp(-rng.normal(-4.0, 1.5, (B, H, W, K))))
+    yp[..., K:] = rng.uniform(0, 60, (B, H, W, Lo.Cp - K))
+    yt_d, yp_d = torch.from_numpy(yt).to(cuda), torch.from_numpy(yp).to(cuda)
+    whole = ops.loss_partials(L, yt_d, yp_d, True).clone()
+    again = ops.loss_partials(L, yt_d, yp_d, True).clone()
+    assert torch.equal(whole, again)                                               # fixed-order reductions: reproducible
+    parts = sum(ops.loss_partials(L, yt_d[a:b], yp_d[a:b], True).clone() for a, b in ((0, 5), (5, 20), (20, 32)))
+    # additive over shards up to the rounding of the short fp32 chains inside a thread (everything above them is fp64)
+    assert torch.allclose(parts, whole, rtol=2e-6, atol=0)
+    total = float(ops.loss_finalize(L, whole)[0])
+    assert total == pytest.approx(loss_np.total_loss(Lo, yt, yp)[0], rel=RTOL)
+
+
+def test_targets_above_one_are_masked(cuda):
+    """Y > 1 belongs to neither the positive nor the negative mask (loss.py:35-36).  The render never produces it, but the
+    kernel must still honour it (its packed fast path redoes such pixels channel by channel)."""
+    from cvmhot import ops
+    from cvmhot.layout import layout_from_params
+    from cvmhot.models.centernet import CenternetParams
+    H, W, K, B = 16, 24, 10, 2
+    p = CenternetParams(K, True)
+    p.INPUT_HEIGHT, p.INPUT_WIDTH = H * p.R, W * p.R
+    Lo = make_layout(H, W, K, "N")
+    data = synth.make_batch(Lo, 5, B)
+    yt = np.stack([render_np.render_image(Lo, data["boxes"][b], data["cls"][b], data["ignore"][b]) for b in range(B)])
+    yt[0, 3, 4, 2] = 1.5
+    yt[1, 7, 7, 0] = 2.0
+    yt[1, 7, 7, 9] = 1.0000001
+    out = ops.loss_finalize(layout_from_params(p), ops.loss_partials(layout_from_params(p), torch.from_numpy(yt).to(cuda),
+                                                                     torch.from_numpy(data["y_pred"]).to(cuda), True))
+    assert float(out[0]) == pytest.approx(loss_np.total_loss(Lo, yt, data["y_pred"])[0], rel=RTOL)

@@ -116,3 +116,51 @@ def test_render_many_objects_and_chunks(cuda):
     rec, offs = pack_objects([boxes], [cls])
     y = ProcessImages(p).render_packed(layout_from_params(p), rec, offs, *pack_boxes([np.zeros((0, 4))])).cpu().numpy()
     _close(y[0], render_np.render_image(Lo, boxes, cls, []))
+
+
+def test_render_properties_full_size(cuda):
+    """BASELINE configs[1] shape (B sampled down to 48): size-independent properties of the render, plus parity of a few
+    images against the oracle.  Every object centre holds exactly 1.0 in its class plane (the loss's `== 1` test), heat
+    lies in [0, 1], weights are <= 1 and exactly 0 inside ignore boxes, regression channels are zero away from centres,
+    and rendering is idempotent / independent of the batch an image sits in."""
+    import bench
+    from cvmhot import ops
+    from cvmhot.layout import layout_from_params
+    from cvmhot.models.centernet.processor import pack_boxes, pack_objects
+    H, W, K, B = 128, 384, 10, 48
+    p = _params(K, True, H, W)
+    L = layout_from_params(p)
+    Lo = make_layout(H, W, K, "N")
+    boxes, cls, ign = bench.gen_objects(0, B)
+    rec, offs = pack_objects(list(boxes), list(cls))
+    irec, ioffs = pack_boxes(list(ign))
+    dev = cuda
+    args = (ops.to_device_records(rec, ops.OBJ_DTYPE, dev), torch.from_numpy(offs).to(dev), B,
+            ops.to_device_records(irec, ops.BOX_DTYPE, dev), torch.from_numpy(ioffs).to(dev))
+    y = ops.render_gt(L, *args)
+    y2 = ops.render_gt(L, *args)
+    assert torch.equal(y, y2)                                                     # deterministic
+    heat, wts = y[..., :K], y[..., -1]
+    assert float(heat.min()) >= 0.0 and float(heat.max()) == 1.0 and float(wts.max()) <= 1.0
+    cx, cy = bench.centres(boxes)
+    bi = np.repeat(np.arange(B), boxes.shape[1])
+    at_centres = heat[torch.from_numpy(bi).to(dev), torch.from_numpy(cy.reshape(-1)).to(dev),
+                      torch.from_numpy(cx.reshape(-1)).to(dev), torch.from_numpy(cls.reshape(-1).astype(np.int64)).to(dev)]
+    big_enough = torch.from_numpy((boxes[..., 2] >= 2).reshape(-1) & (boxes[..., 3] >= 2).reshape(-1)).to(dev)
+    assert bool((at_centres[big_enough] == 1.0).all())                            # exact peaks (objects < 2 px draw nothing)
+    reg = y[..., K:-1].abs().sum(dim=-1)
+    mask = torch.zeros((B, H, W), dtype=torch.bool, device=dev)
+    mask[torch.from_numpy(bi).to(dev), torch.from_numpy(cy.reshape(-1)).to(dev), torch.from_numpy(cx.reshape(-1)).to(dev)] = True
+    assert float(reg[~mask].max()) == 0.0                                         # targets only at centre pixels
+    for b in (0, 17, 47):
+        for (x, yy, w, h) in ign[b]:
+            sl = wts[b, max(int(yy), 0):int(yy + h), max(int(x), 0):int(x + w)]
+            assert sl.numel() == 0 or float(sl.abs().max()) == 0.0                # ignore areas (input px used as mask px)
+        ref = render_np.render_image(Lo, boxes[b], cls[b], ign[b])
+        _close(y[b].cpu().numpy(), ref)
+    # an image renders the same alone as inside the batch
+    r1, o1 = pack_objects([boxes[17]], [cls[17]])
+    i1, io1 = pack_boxes([ign[17]])
+    y17 = ops.render_gt(L, ops.to_device_records(r1, ops.OBJ_DTYPE, dev), torch.from_numpy(o1).to(dev), 1,
+                        ops.to_device_records(i1, ops.BOX_DTYPE, dev), torch.from_numpy(io1).to(dev))
+    assert torch.equal(y17[0], y[17])
