@@ -52,6 +52,8 @@ def lib():
     L.cvm_last_error.argtypes = []
     L.cvm_version.restype = i32
     L.cvm_version.argtypes = []
+    L.cvm_prepare_objects.restype = i32
+    L.cvm_prepare_objects.argtypes = [vp, vp, vp, vp, i32, f64, f64, f64, vp, vp, vp, vp, vp]
     L.cvm_render_gt.restype = i32
     L.cvm_render_gt.argtypes = [LP, vp, vp, vp, vp, i32, vp, vp]
     L.cvm_render_prev_hm.restype = i32
@@ -81,7 +83,7 @@ def lib():
 
 
 EXPORTS = [
-    "cvm_last_error", "cvm_version", "cvm_render_gt", "cvm_render_prev_hm", "cvm_fill_heatmap_inplace", "cvm_loss_workspace_bytes",
+    "cvm_last_error", "cvm_version", "cvm_prepare_objects", "cvm_render_gt", "cvm_render_prev_hm", "cvm_fill_heatmap_inplace", "cvm_loss_workspace_bytes",
     "cvm_loss_fwd", "cvm_loss_finalize", "cvm_loss_bwd", "cvm_decode_topk_workspace_bytes", "cvm_decode_topk",
     "cvm_decode_window9_workspace_bytes", "cvm_decode_window9", "cvm_semseg_argmax",
 ]

@@ -122,6 +122,16 @@ class ProcessImages(IPreProcessor):
             b_ign.append(ign)
         return self.render_packed(L, *pack_objects(b_boxes, b_cls), *pack_boxes(b_ign), out=out)
 
+    def render_raw_batch(self, raw_boxes, raw_cls, raw_offsets, out=None, raw_track=None):
+        """Device-resident raw labels -> y_true, no host loop: raw_boxes [n,4] float64 CUDA (x, y, w, h in input px, NOT
+        yet clipped), raw_cls [n] int32 CUDA (OD_CLASS_IDX), raw_offsets [B+1] int32 CUDA.  The clip + MIN_BOX_AREA filter
+        of the reference (processor.py:46-56,241-253) runs on the device (cvm_prepare_objects), then the render."""
+        p = self.params
+        L = layout_from_params(p)
+        objs, offs, ign, ioffs = ops.prepare_objects(raw_boxes, raw_cls, raw_offsets, p.INPUT_WIDTH, p.INPUT_HEIGHT,
+                                                     p.MIN_BOX_AREA, raw_track)
+        return ops.render_gt(L, objs, offs, int(raw_offsets.numel()) - 1, ign, ioffs, out=out)
+
     def render_packed(self, L, rec, offsets, ign_rec, ign_offsets, out=None):
         dev = self.device
         B = len(offsets) - 1

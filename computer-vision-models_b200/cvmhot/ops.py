@@ -78,6 +78,32 @@ def _workspace(device, nbytes, tag):
     return ws
 
 
+# ---- pre-processing front-end ----------------------------------------------------------------------------------------
+def prepare_objects(raw_boxes, raw_cls, raw_offsets, img_w, img_h, min_box_area, raw_track=None):
+    """Device-side clip_to_img + MIN_BOX_AREA filter (reference processor.py:46-56,241-253) for a whole batch.
+
+    raw_boxes [n,4] float64, raw_cls [n] int32, raw_offsets [B+1] int32 (all CUDA), raw_track [n,2] float32 or None.
+    Returns (objs, obj_offsets, ignore, ign_offsets): uint8 record tensors + int32 offsets, ready for render_gt."""
+    _need_cuda(raw_boxes, "raw_boxes", torch.float64)
+    _need_cuda(raw_cls, "raw_cls", torch.int32)
+    _need_cuda(raw_offsets, "raw_offsets", torch.int32)
+    if raw_track is not None:
+        _need_cuda(raw_track, "raw_track", torch.float32)
+    dev = raw_boxes.device
+    n, B = int(raw_cls.numel()), int(raw_offsets.numel()) - 1
+    if raw_boxes.numel() != 4 * n or not raw_boxes.is_contiguous():
+        raise _lib.CvmError("raw_boxes must be a contiguous [n,4] float64 tensor")
+    objs = torch.empty(max(n, 1) * OBJ_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    ignore = torch.empty(max(n, 1) * BOX_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    obj_offsets = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    ign_offsets = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    rc = _lib.lib().cvm_prepare_objects(_ptr(raw_boxes), _ptr(raw_cls), _ptr(raw_track), _ptr(raw_offsets), B, float(img_w),
+                                        float(img_h), float(min_box_area), _ptr(objs), _ptr(obj_offsets), _ptr(ignore),
+                                        _ptr(ign_offsets), _stream())
+    _lib.check(rc, "cvm_prepare_objects")
+    return objs, obj_offsets, ignore, ign_offsets
+
+
 # ---- render ----------------------------------------------------------------------------------------------------------
 def render_gt(layout: Layout, objs_dev, obj_offsets_dev, B, ignore_dev=None, ign_offsets_dev=None, out=None):
     """y_true [B,H,W,Ct] from device object records (see pack in models/centernet/processor.py)."""

@@ -5,6 +5,7 @@
  * of this path is a handful of Python call sites.  Each entry point below replaces the tensor math behind one
  * of them (paths relative to the reference root):
  *
+ *   cvm_prepare_objects  clip_to_img + MIN_BOX_AREA filter of ProcessImages.process (processor.py:46-56,241-253), batched
  *   cvm_render_gt        fill_heatmap (models/centernet/processor.py:17-38) + the render part of
  *                        ProcessImages.process (processor.py:264-334) incl. calc_img_data's centre math (:58-67)
  *   cvm_render_prev_hm   CenterTrackerProcess.gen_prev_heatmap (models/centertracker/processor.py:22-41)
@@ -99,6 +100,17 @@ typedef struct cvm_roi {
 
 const char* cvm_last_error(void);
 int cvm_version(void);
+
+/* ---- pre-processing front-end ------------------------------------------------------------------------------------ */
+/* Raw labelled boxes -> render inputs, on the device: clip_to_img (processor.py:46-56) and the MIN_BOX_AREA filter
+ * (processor.py:241-253) of ProcessImages.process for a whole batch; replaces the per-sample host loop of
+ * BaseDataGenerator._process_batch (data/base_data_generator.py:29-48).  raw_boxes [n,4] fp64 (x, y, w, h in input px),
+ * raw_cls [n] (OD_CLASS_IDX), raw_track [n,2] or NULL, raw_offsets [B+1] (image b owns [raw_offsets[b], raw_offsets[b+1])).
+ * Outputs (capacity n each): objs / obj_offsets [B+1] in list order, boxes at or below the area limit become ignore
+ * areas (ignore / ign_offsets [B+1]).  All pointers are device pointers. */
+int cvm_prepare_objects(const double* raw_boxes, const int32_t* raw_cls, const float* raw_track, const int32_t* raw_offsets,
+                        int B, double img_w, double img_h, double min_box_area, cvm_obj* objs, int32_t* obj_offsets,
+                        cvm_box* ignore, int32_t* ign_offsets, void* stream);
 
 /* ---- render -------------------------------------------------------------------------------------------------- */
 /* objs[obj_offsets[b] .. obj_offsets[b+1]) are image b's objects in list order (order matters for the centre

@@ -164,3 +164,44 @@ def test_render_properties_full_size(cuda):
     y17 = ops.render_gt(L, ops.to_device_records(r1, ops.OBJ_DTYPE, dev), torch.from_numpy(o1).to(dev), 1,
                         ops.to_device_records(i1, ops.BOX_DTYPE, dev), torch.from_numpy(io1).to(dev))
     assert torch.equal(y17[0], y[17])
+
+
+def test_device_front_end_vs_real_process_golden(cuda, golden_dir):
+    """cvm_prepare_objects + cvm_render_gt on RAW (unclipped, unfiltered) boxes reproduce, bit for bit, the y_true the real
+    ProcessImages.process produced from the same raw boxes; in a batch with an empty image in the middle too; and the
+    records equal the host mirror of the filter."""
+    from cvmhot import ops
+    from cvmhot.models.centernet import ProcessImages
+    from cvmhot.models.centernet.processor import pack_boxes, pack_objects
+    for name in ("render_process_a", "render_process_b", "render_process_empty"):
+        g = np.load(os.path.join(golden_dir, name + ".npz"))
+        p = _params(6, False, int(g["in_h"]) // 2, int(g["in_w"]) // 2)
+        proc = ProcessImages(p)
+        raw1 = g["raw_boxes"].reshape(-1, 4).astype(np.float64)
+        cls1 = g["cls"].reshape(-1).astype(np.int32)
+        n1 = len(cls1)
+        # batch: the sample, an image without objects, the sample again
+        raw = np.concatenate([raw1, raw1]) if n1 else np.zeros((0, 4))
+        cls = np.concatenate([cls1, cls1]) if n1 else np.zeros((0,), np.int32)
+        offs = np.array([0, n1, n1, 2 * n1], np.int32)
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+        y = proc.render_raw_batch(dev(raw.reshape(-1, 4)), dev(cls), dev(offs))
+        y = y.cpu().numpy()
+        assert np.array_equal(y[0], g["y_true"]) and np.array_equal(y[2], g["y_true"])
+        assert float(np.abs(y[1][..., :-1]).max()) == 0.0 and float(y[1][..., -1].min()) == 1.0
+        if n1 == 0:
+            continue
+        # record-level check against the host mirror of the filter
+        objs_d, offs_d, ign_d, ioffs_d = ops.prepare_objects(dev(raw), dev(cls), dev(offs), p.INPUT_WIDTH, p.INPUT_HEIGHT,
+                                                             p.MIN_BOX_AREA)
+        boxes, c, ign = proc.filter_objects([{"box2d": list(bx), "obj_class": int(k)} for bx, k in zip(raw1, cls1)],
+                                            p.INPUT_WIDTH, p.INPUT_HEIGHT)
+        rec, roffs = pack_objects([boxes, [], boxes], [c, [], c])
+        irec, ioffs = pack_boxes([ign, [], ign])
+        assert np.array_equal(offs_d.cpu().numpy(), roffs) and np.array_equal(ioffs_d.cpu().numpy(), ioffs)
+        got = objs_d.cpu().numpy()[:rec.size * ops.OBJ_DTYPE.itemsize].view(ops.OBJ_DTYPE)
+        for f in ("x", "y", "w", "h", "cls"):
+            assert np.array_equal(got[f], rec[f]), f
+        goti = ign_d.cpu().numpy()[:irec.size * ops.BOX_DTYPE.itemsize].view(ops.BOX_DTYPE)
+        for f in ("x", "y", "w", "h"):
+            assert np.array_equal(goti[f], irec[f]), f
