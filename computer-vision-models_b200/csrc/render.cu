@@ -12,7 +12,7 @@
 // (object, 32-column segment) work unit walks the unit's rows, lane = column, and max-/min-combines the gaussian into the
 // chunk with shared integer atomics on the float bit patterns (windows of different objects overlap); then ignore areas
 // and the handful of regression targets at centre pixels are written, and ONE bulk async copy (TMA engine: UBLKCP,
-// shared -> global) streams the chunk out while the CTA builds the next one in the other buffer.  No store instruction
+// shared -> global) streams the chunk out while the SM's other CTA builds its chunk.  No store instruction
 // touches global memory on the fast path.  All gaussian math is fp64 like the reference's (scalar fp64 stored as fp32);
 // the separable factors exp(-ax), exp(-ay) are tabulated (per image / per chunk), see render_kernel.
 #include <stdlib.h>
@@ -25,7 +25,11 @@ constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxObjSmem = 64;   // objects are processed in batches of this many
 constexpr int kMaxIgnSmem = 16;     // ignore boxes cached in shared memory per image (more are read from global)
-constexpr int kChunkBytes = 43008;   // staging buffer size: two buffers per CTA, two CTAs per SM
+#ifndef CVM_RENDER_BUFFERS
+#define CVM_RENDER_BUFFERS 1
+#endif
+constexpr int kBuffers = CVM_RENDER_BUFFERS;   // staging buffers per CTA (two CTAs per SM: one builds while the other's chunk streams out)
+constexpr int kChunkBytes = 86016 / kBuffers;
 constexpr int kMaxUnits = 512;       // (object, 32-column segment) work units per chunk and object batch
 constexpr int kColTab = 1024;        // entries of the per-image column-factor table (objects that do not fit use exp)
 constexpr int kRowTab = 1024;        // entries of the per-image row-factor table
@@ -123,7 +127,7 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-extern __shared__ __align__(128) unsigned char g_render_smem[];   // two staging buffers of kChunkBytes
+extern __shared__ __align__(128) unsigned char g_render_smem[];   // kBuffers staging buffers of kChunkBytes
 
 // max / min combine of a float into shared memory through integer atomics on the bit pattern: non-negative floats order
 // like signed ints, negative floats order inversely like unsigned ints, and each of the two operations keeps the cell
@@ -159,9 +163,6 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
 
     const long long G = gridDim.x, g = blockIdx.x;
     const long long c0 = g * p.n_chunks / G, c1 = (g + 1) * p.n_chunks / G;
-    long long img = c0 / cpi;
-    int ci = (int)(c0 - img * cpi);
-    int ya = (ci * P) / W, xa = ci * P - ya * W;   // row / column of the chunk's first pixel, kept incrementally
     // pattern fill: thread t < n_fill writes the float4s t, t + n_fill, ...; n_fill is a multiple of Cout, so the channel
     // phase of its float4 -- and with it the value (zeros, 1.0 where the weights channel falls) -- never changes
     const int n_fill = (kThreads / Cout) * Cout;
@@ -174,32 +175,34 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
         fill_v.w = ((r + 3) % Cout == wch) ? 1.f : 0.f;
     }
     const bool scatter = p.off_class >= 0 || p.off_roff >= 0 || p.off_box >= 0 || p.off_track >= 0;
-    long long loaded_img = -1;   // image whose objects the batch in sobj belongs to
-    int loaded_base = -1;        // first object of that batch
-    long long ign_img = -1;      // image whose ignore boxes sit in s_ign
-    long long off_img = -1;      // image whose ranges are in the registers below
-    int o_begin = 0, o_end = 0, i_begin = 0, n_ign = 0;
-    int buf = 0;
+    int loaded_img = -1;         // image whose per-image state (ranges, ignore boxes, first object batch) is loaded
+    int loaded_base = -1;        // first object of the batch in sobj
+    int o_begin = 0, o_end = 0, i_begin = 0, n_ign = 0, n_batches = 0;
     int lk = 0;                  // list builds so far (parity picks the counter)
+    const int step_rows = P / W, step_cols = P - step_rows * W;   // how (ya, xa) advance from one chunk to the next
     if (tid < 2) s_nunits[tid] = 0;
     __syncthreads();
 
-    for (long long c = c0; c < c1; ++c) {
+    int img = (int)(c0 / cpi);
+    int ci = (int)(c0 - (long long)img * cpi);
+    int ya = (ci * P) / W, xa = ci * P - ya * W;   // row / column of the chunk's first pixel, kept incrementally
+    const int n_local = (int)(c1 - c0);
+    for (int it = 0; it < n_local; ++it) {
         const int q0 = ci * P, q1 = min(HW, q0 + P), npx = q1 - q0;
         int yb = ya;   // row of the chunk's last pixel
         for (int t = xa + npx - 1; t >= W; t -= W) ++yb;
-        float* const st = stage0 + (size_t)buf * (kChunkBytes / 4);
-        if (off_img != img) {   // object / ignore-box ranges of the image: fetched once per image, not once per chunk
+        float* const st = stage0 + (size_t)(kBuffers > 1 ? (it & 1) : 0) * (kChunkBytes / 4);
+        const bool new_img = loaded_img != img;
+        if (new_img) {   // object / ignore-box ranges of the image: fetched once per image, not once per chunk
             o_begin = p.obj_offsets[img];
             o_end = p.obj_offsets[img + 1];
+            n_batches = (o_end - o_begin + kMaxObjSmem - 1) / kMaxObjSmem;
             n_ign = i_begin = 0;
             if (p.ignore != nullptr && has_w) {
                 i_begin = p.ign_offsets[img];
                 n_ign = p.ign_offsets[img + 1] - i_begin;
             }
-            off_img = img;
         }
-        const int n_batches = (o_end - o_begin + kMaxObjSmem - 1) / kMaxObjSmem;
 
         // ---- phase 1: pattern fill (heat = 0, weights = 1, regression targets = 0; processor.py:267-268) ----
         if (tid < n_fill && !(p.dbg_skip & 4)) {
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
             float4* s4 = reinterpret_cast<float4*>(st);
             for (int f = tid; f < n4; f += n_fill) s4[f] = fill_v;
         }
-        if (ign_img != img) {   // clamp the ignore boxes once per image (read after the barriers below)
+        if (new_img) {   // clamp the ignore boxes once per image (read after the barriers below)
             if (tid < min(n_ign, kMaxIgnSmem)) {
                 const cvm_box bx = p.ignore[i_begin + tid];
                 s_ign[tid][0] = max((int)bx.x, 0);
@@ -215,14 +218,13 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
                 s_ign[tid][2] = max((int)bx.y, 0);
                 s_ign[tid][3] = min(max((int)(bx.y + bx.h), 0), p.H);
             }
-            ign_img = img;
         }
 
         for (int bi = 0; bi < n_batches; ++bi) {   // one batch in the common case
             const int base = o_begin + bi * kMaxObjSmem;
             const int n = min(kMaxObjSmem, o_end - base);
             const int par = (lk++) & 1;
-            if (loaded_img != img || loaded_base != base) {
+            if (new_img || loaded_base != base) {
                 // ---- once per image (and object batch): derived records, scatter winners, column factors ----
                 if (bi > 0) __syncthreads();   // the previous batch is still being read
                 if (tid < n) derive(p.objs[base + tid], p, sobj[tid]);
@@ -292,7 +294,6 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
                         }
                     }
                 }
-                loaded_img = img;
                 loaded_base = base;
             }
             // ---- work units of this chunk ----
@@ -399,15 +400,26 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
         }
 
         // ---- stream the chunk out ----
-        float* const dst = p.out + ((size_t)img * HW + q0) * Cout;
         if (p.bulk) {
             if (!(p.dbg_skip & 16)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk engine
-            // the next chunk refills the other buffer right after the barrier: its bulk store must have finished reading
-            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncthreads();   // ---- barrier B ----
-            if (tid == 0 && !(p.dbg_skip & 2)) bulk_s2g(dst, st, (uint32_t)(npx * Cout * 4));
+            if (kBuffers > 1) {
+                // the next chunk refills the other buffer right after the barrier: its bulk store must have finished reading
+                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncthreads();   // ---- barrier B: the chunk is complete ----
+                if (tid == 0 && !(p.dbg_skip & 2)) bulk_s2g(p.out + ((size_t)img * HW + q0) * Cout, st, (uint32_t)(npx * Cout * 4));
+            } else {
+                __syncthreads();   // ---- barrier B: the chunk is complete ----
+                if (tid == 0) {
+                    if (!(p.dbg_skip & 2)) bulk_s2g(p.out + ((size_t)img * HW + q0) * Cout, st, (uint32_t)(npx * Cout * 4));
+                    // the next chunk is built in the same buffer: the bulk engine must have finished reading it (meanwhile
+                    // the SM's other CTA builds its chunk)
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+                __syncthreads();   // ---- barrier C ----
+            }
         } else {
             __syncthreads();
+            float* const dst = p.out + ((size_t)img * HW + q0) * Cout;
             const int nf = npx * Cout;
             if (p.vec) {   // 16-byte aligned chunk: 128-bit streaming stores
                 const float4* s4 = reinterpret_cast<const float4*>(st);
@@ -418,13 +430,18 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
             }
             __syncthreads();   // the buffer is refilled two chunks later, but sobj / lists are reused by the next one
         }
-        buf ^= 1;
+        loaded_img = img;
         if (++ci == cpi) {
             ci = 0;
             ++img;
             ya = xa = 0;
         } else {
-            for (xa += P; xa >= W; xa -= W) ++ya;
+            ya += step_rows;
+            xa += step_cols;
+            if (xa >= W) {
+                xa -= W;
+                ++ya;
+            }
         }
     }
     if (p.bulk && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA retires
@@ -447,7 +464,7 @@ int launch_render(const RenderParams& p0, int B, cudaStream_t st) {
     p.vec = p.bulk;
     if (const char* e = getenv("CVM_RENDER_SKIP")) p.dbg_skip = atoi(e);
     if (p.dbg_skip & 8) p.bulk = 0;   // experiment: plain stores instead of bulk copies
-    const size_t smem = 2 * (size_t)kChunkBytes;
+    const size_t smem = (size_t)kBuffers * kChunkBytes;
     CVM_CHECK_CUDA(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = 2LL * cvm_num_sms();
     if (grid > p.n_chunks) grid = p.n_chunks;
