@@ -6,7 +6,7 @@ from cvmhot import ops
 from cvmhot.layout import layout_from_params
 from cvmhot.models.centernet import CenternetParams
 from cvmhot.models.centernet.processor import pack_boxes, pack_objects
-B = 256
+B = int(os.environ.get("CVM_B", "256"))
 p = CenternetParams(10, per_class_heatmap=True); p.INPUT_HEIGHT, p.INPUT_WIDTH = 256, 768
 L = layout_from_params(p)
 dev = torch.device("cuda", 0)
