@@ -4,16 +4,16 @@
 //
 // Bound: HBM reads.  Algorithmic bytes per image: 4*H*W*pred_stride, read exactly once.
 //
-// Kernel 1 (decode_scan_kernel).  The batch is one flat list of steps (T = 480 consecutive pixels of one image, all
-// channels: a contiguous piece of y_pred).  The list is cut into gridDim.x equal contiguous ranges, one persistent CTA
+// Kernel 1 (decode_scan_kernel).  The batch is one flat list of steps (one or two granules of 480 consecutive pixels of one
+// image, all channels: a contiguous piece of y_pred).  The list is cut into gridDim.x equal contiguous ranges, one persistent CTA
 // per SM and range, so every SM streams the same number of bytes.  A loader warp feeds a shared-memory ring of granules
-// (Pg pixels each) with 1-D bulk async copies (TMA engine: UBLKCP + mbarrier, full/empty barrier pair per slot),
+// with 1-D bulk async copies (TMA engine: UBLKCP + mbarrier, full/empty barrier pair per slot),
 // several granules ahead.  Fifteen scanner warps walk the steps WITHOUT any CTA-wide barrier: per step every lane owns
-// one pixel, takes the maximum over the heatmap channels (vector shared loads, no bank conflicts) and compares it ONCE
-// with the CTA's running threshold score.  A lane whose pixel reaches the threshold tests it one step later, when the
-// pixels after it have arrived: the 3x3 test reads the eight neighbours out of the ring (W + 1 pixels of history and
-// lookahead stay resident; for maps too wide for that they are read from global memory).  Peaks are appended to a
-// shared-memory candidate buffer as 64-bit keys (score bits << 32 | ~flat index): a total order with no ties, equal
+// one pixel per granule of the step, takes the maximum over its heatmap channels (vector shared loads, no bank conflicts)
+// and compares it ONCE with the CTA's running threshold score.  A step is scanned when the W + 1 pixels after it have
+// arrived too, so a pixel that reaches the threshold is tested right away: the 3x3 test reads the eight neighbours out
+// of the ring (W + 1 pixels of history and lookahead stay resident; for maps too wide for that they are read from global
+// memory).  Peaks are appended to a shared-memory candidate buffer as 64-bit keys (score bits << 32 | ~flat index): a total order with no ties, equal
 // to (score desc, flat index asc).  A score histogram of the appended peaks raises the threshold (one warp scans it
 // between steps).  Only two rare events gather the scanner warps on a named barrier: the buffer passing its mark (exact
 // radix select, keeps the best K) and the end of an image, where the CTA writes its <= K best keys of that image
@@ -662,25 +662,16 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
     int st = st0;
     int gseq = lead;         // sequence number of the first granule of the current step
     int cur_slot = lead;     // its ring slot (lead <= halo_g < S)
-    Hit prev[GPS];           // this lane's pixels of the previous step that reached the threshold: wait for their 3x3 test
-#pragma unroll
-    for (int k = 0; k < GPS; ++k) {
-        prev[k].mask = 0ull;
-        prev[k].q = prev[k].rp = 0;
-    }
-
     for (int i = 0; i < n_local; ++i) {
         const int g0 = st * GPS;                                 // first granule of the step inside the image
         const int gc = min(GPS, gpi - g0);                        // granules in this step (the last step of an image may be short)
         // last granule of this image that this CTA fetches
         const int seq_last = min(gseq + (gpi - 1 - g0), n_load - 1);
-        // this step's granules, and the lookahead of the previous step's pixels (W + 1 pixels past its end)
+        // this step's granules and their lookahead (W + 1 pixels past the end of the step): a pixel is scanned and, if it
+        // reaches the threshold, tested in the same step
         DBG_STATE(100 + i * 1000);
-        wait_until(p, z, min(max(gseq + gc - 1, gseq - 1 + hg), seq_last) + 1);
+        wait_until(p, z, min(gseq + gc - 1 + hg, seq_last) + 1);
         DBG_STATE(101 + i * 1000);
-        test_hits<GPS>(p, img, prev, z.thr_f);
-        // this step: one compare per pixel
-        DBG_STATE(102 + i * 1000);
         Hit cur[GPS];
 #pragma unroll
         for (int k = 0; k < GPS; ++k) {
@@ -695,12 +686,15 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
                 if (pixel_max<STRIDE, HM>(px, p.hm) >= z.thr_f) cur[k].mask = channel_mask<HM>(px, p.hm, z.thr_f);
             }
         }
-        // the next step tests this step's pixels and needs halo_g granules of history before it: the rest is dead
-        release_until(p, z, gseq - hg);
+        DBG_STATE(102 + i * 1000);
+        test_hits<GPS>(p, img, cur, z.thr_f);
+        const bool segment_end = (st + 1 == spi) || (i + 1 == n_local);
+        const bool image_end = st + 1 == spi;
+        // the next step needs halo_g granules of history before its first granule: the rest is dead
+        release_until(p, z, segment_end ? (image_end ? gseq + gc : n_load) : gseq + gc - hg);
         __syncwarp();   // converged: the control word below is one broadcast load, the same pair for all lanes
         const uint2 ctrl = load_ctrl(h);
         z.thr_f = __uint_as_float(ctrl.x);   // stale values are still valid bounds
-        const bool segment_end = (st + 1 == spi) || (i + 1 == n_local);
         DBG_STATE(103 + i * 1000);
         if (!segment_end) {
             if (warp == 1) scan_threshold(h, sm_shist(p), p.K, lane);
@@ -708,20 +702,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
                 gather(p, false, 0);
                 z.thr_f = __uint_as_float(load_ctrl(h).x);
             }
-#pragma unroll
-            for (int k = 0; k < GPS; ++k) prev[k] = cur[k];
             ++st;
         } else {
-            // drain: test this step's hits now (the lookahead, if any, belongs to the next CTA's range and was fetched too)
-            wait_until(p, z, min(gseq + gc - 1 + hg, seq_last) + 1);
-            test_hits<GPS>(p, img, cur, z.thr_f);
-            const bool image_end = st + 1 == spi;
-            release_until(p, z, image_end ? gseq + gc : n_load);   // the rest of the image / of the range is dead
             if (lane == 0) atomicAdd(&h->seg_done, 1);
             gather(p, true, (int)(img - img0));
             z.thr_f = __uint_as_float(p.thr0_bits);
-#pragma unroll
-            for (int k = 0; k < GPS; ++k) prev[k].mask = 0ull;
             if (image_end) {
                 st = 0;
                 ++img;
@@ -893,31 +878,31 @@ int plan_decode(const cvm_layout* L, int stride, int B, int K, Plan* t) {
         if (fixed + 4 * gran_bytes > (size_t)kSmemBudget) continue;
         int S = (int)(((size_t)kSmemBudget - fixed) / gran_bytes);
         if (S > kMaxSlots) S = kMaxSlots;
-        // ring mode keeps halo_g + gps + max(gps, halo_g) granules resident (history, the tested step, the scanned step /
-        // the lookahead of the tested one); global-neighbour mode keeps 2 * gps; both want two more in flight
+        // ring mode keeps halo_g + gps + halo_g granules resident (history, the step, its lookahead); global-neighbour mode
+        // keeps the step; both want at least two, better three, more in flight
         const int hg = (W + 1 + T - 1) / T;
         t->gps = 0;
         for (int gps = gps_want; gps >= 1 && !t->gps; --gps) {
-            const int need = hg + gps + (gps > hg ? gps : hg) + 2;
+            const int need = hg + gps + hg + 2;
             if (S >= need) {
                 t->gps = gps;
                 t->ring_nb = 1;
                 t->halo_g = hg;
-                t->S = need;
+                t->S = S > need ? need + 1 : need;
             }
         }
         if (!t->gps) {
-            t->gps = S >= 6 ? gps_want : 1;
+            t->gps = S >= 4 ? gps_want : 1;
             t->ring_nb = 0;
             t->halo_g = 0;
-            t->S = S < 2 * t->gps + 2 ? S : 2 * t->gps + 2;
+            t->S = S < t->gps + 2 ? S : t->gps + 2;
         }
         t->gran_floats = T * stride;
         break;
     }
     {
         const int v = env_int("CVM_DECODE_S", 0);   // experiment knob: ring depth
-        const int need = t->ring_nb ? t->halo_g + t->gps + (t->gps > t->halo_g ? t->gps : t->halo_g) + 1 : 2 * t->gps;
+        const int need = t->ring_nb ? 2 * t->halo_g + t->gps + 1 : t->gps + 1;
         if (v >= need && v <= kMaxSlots && smem_bytes(v, t->gran_floats, t->cap, K) <= (size_t)kSmemBudget) t->S = v;
     }
     t->T = T;
