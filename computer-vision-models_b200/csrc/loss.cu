@@ -32,6 +32,7 @@ struct LossParams {
     int n_fields;
     int f_off[CVM_MAX_FIELDS], f_size[CVM_MAX_FIELDS], f_kind[CVM_MAX_FIELDS];
     int use_bulk;
+    int n_stages;      // ring depth of the fast kernel
     double* block_partials;   // [gridDim.x][CVM_NPART]
 };
 
@@ -321,22 +322,29 @@ __device__ __forceinline__ f2 mul2(f2 a, f2 b) {
 // ---- fast path: channel counts known at compile time, one pixel per thread ------------------------------------------
 // All shared-memory offsets become immediates, the heatmap loop is fully unrolled (HM independent element chains per
 // thread) and the rare "this pixel holds a peak" work is taken out of the hot loop.
+// Fast forward kernel: 160 consumer threads (one pixel per thread and span) + the loader warp, and a ring as deep as lets two
+// CTAs share an SM (5 stages for the CenterNet layouts).  Measured on B200 at the BASELINE shape: 256 threads x 3 stages
+// 0.260 ms, 192 x 4 0.248 ms, 160 x 5 0.245 ms: bytes in flight matter more than consumer warps.
+constexpr int kFastThreads = 160;
+constexpr int kFastStages = 5;    // most stages the barrier arrays hold; LossParams::n_stages <= this are used
+
 template <int HM, int ST_T, int ST_P>
-__global__ void __launch_bounds__(kThreads + 32) loss_fwd_fast_kernel(const LossParams p) {
+__global__ void __launch_bounds__(kFastThreads + 32) loss_fwd_fast_kernel(const LossParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t full_bar[kStages];    // loader -> consumers: span arrived
-    __shared__ uint64_t empty_bar[kStages];   // consumers -> loader: all consumer warps are done with the stage
-    __shared__ double red[kThreads / 32][CVM_NPART];
+    __shared__ uint64_t full_bar[kFastStages];    // loader -> consumers: span arrived
+    __shared__ uint64_t empty_bar[kFastStages];   // consumers -> loader: all consumer warps are done with the stage
+    __shared__ double red[kFastThreads / 32][CVM_NPART];
 
     float* const ring = reinterpret_cast<float*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int TP = kThreads;  // one pixel per consumer thread per span
-    constexpr int kConsumerWarps = kThreads / 32;
+    const int n_stages = p.n_stages;
+    constexpr int TP = kFastThreads;  // one pixel per consumer thread per span
+    constexpr int kConsumerWarps = kFastThreads / 32;
     constexpr size_t t_floats = (size_t)TP * ST_T;
     constexpr size_t stage_floats = (size_t)TP * (ST_T + ST_P);
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < n_stages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], kConsumerWarps);
         }
@@ -351,13 +359,13 @@ __global__ void __launch_bounds__(kThreads + 32) loss_fwd_fast_kernel(const Loss
     for (int k = 0; k < CVM_NPART; ++k) v[k] = 0.0;
 
     if (warp == kConsumerWarps) {
-        // ---- loader warp: span `it` of this CTA goes to stage it % kStages once every consumer warp has released it ----
+        // ---- loader warp: span `it` of this CTA goes to stage it % n_stages once every consumer warp has released it ----
         int s = 0;
         uint32_t e_parity = 0;
         for (int it = 0;; ++it) {
             const long long span = blockIdx.x + (long long)it * gstride;
             if (span >= p.n_spans) break;
-            if (it >= kStages) mbar_wait(&empty_bar[s], e_parity);
+            if (it >= n_stages) mbar_wait(&empty_bar[s], e_parity);
             float* dst_t = ring + (size_t)s * stage_floats;
             float* dst_p = dst_t + t_floats;
             const float* src_t = p.yt + span * (long long)(TP * ST_T);
@@ -377,9 +385,9 @@ __global__ void __launch_bounds__(kThreads + 32) loss_fwd_fast_kernel(const Loss
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full_bar[s]);   // release: the stores above are visible to the waiters
             }
-            if (++s == kStages) {
+            if (++s == n_stages) {
                 s = 0;
-                if (it >= kStages) e_parity ^= 1u;
+                if (it >= n_stages) e_parity ^= 1u;
             }
         }
     } else {
@@ -470,7 +478,7 @@ __global__ void __launch_bounds__(kThreads + 32) loss_fwd_fast_kernel(const Loss
             }
             __syncwarp();   // every lane is done reading the stage
             if (lane == 0) mbar_arrive(&empty_bar[s]);
-            if (++s == kStages) {
+            if (++s == n_stages) {
                 s = 0;
                 f_parity ^= 1u;
             }
@@ -498,12 +506,17 @@ __global__ void __launch_bounds__(kThreads + 32) loss_fwd_fast_kernel(const Loss
 
 template <int HM, int ST_T, int ST_P>
 int launch_loss_fast(LossParams& p, cudaStream_t st, int* grid_out) {
-    p.TP = kThreads;
+    p.TP = kFastThreads;
     p.n_spans = (p.n_pixels + p.TP - 1) / p.TP;
-    const size_t smem = (size_t)kStages * kThreads * (ST_T + ST_P) * 4;
+    const size_t stage_bytes = (size_t)kFastThreads * (ST_T + ST_P) * 4;
+    int n_stages = (int)((size_t)(110 * 1024) / stage_bytes);   // two CTAs per SM
+    if (n_stages > kFastStages) n_stages = kFastStages;
+    if (n_stages < 2) n_stages = 2;
+    p.n_stages = n_stages;
+    const size_t smem = (size_t)n_stages * stage_bytes;
     const int grid = loss_grid(p.n_spans, smem);
     CVM_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_fast_kernel<HM, ST_T, ST_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    loss_fwd_fast_kernel<HM, ST_T, ST_P><<<grid, kThreads + 32, smem, st>>>(p);
+    loss_fwd_fast_kernel<HM, ST_T, ST_P><<<grid, kFastThreads + 32, smem, st>>>(p);
     CVM_CHECK_LAUNCH("loss_fwd_fast_kernel");
     *grid_out = grid;
     return CVM_OK;
