@@ -77,7 +77,7 @@ def test_topk_ties_plateaus_and_sparse_maps(cuda):
 
 
 def test_topk_compaction_stress(cuda):
-    """Dense, slowly rising maps force many threshold raises/compactions inside one stripe."""
+    """Dense, slowly rising maps force many threshold raises and compactions inside one segment."""
     from cvmhot.models.centernet.post_processing import decode_topk
     H, W, C = 128, 384, 10
     Lo = make_layout(H, W, C, "N")
