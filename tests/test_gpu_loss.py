@@ -157,9 +157,13 @@ def _torch_loss64(Lo, yt, yp):
     return total
 
 
-@pytest.mark.parametrize("profile,track,allf", [("N", False, False), ("R", True, False), ("R", False, True)])
-def test_backward_vs_autograd(cuda, profile, track, allf):
-    H, W, K, B = 24, 40, 5, 3
+@pytest.mark.parametrize("profile,track,allf,K,H,W", [
+    ("N", False, False, 5, 24, 40), ("R", True, False, 5, 24, 40), ("R", False, True, 5, 24, 40),
+    # the layouts the fast backward kernel is instantiated for (10 classes: 15/14 and tracker 17/16 channels); 25x41x3
+    # pixels = 19 full 160-pixel spans for the fast kernel + a ragged tail for the generic one
+    ("N", False, False, 10, 25, 41), ("N", True, False, 10, 25, 41), ("N", False, False, 10, 32, 40)])
+def test_backward_vs_autograd(cuda, profile, track, allf, K, H, W):
+    B = 3
     Lo = make_layout(H, W, K, profile, track=track, l_shape=allf, info3d=allf)
     yt, yp = _batch(Lo, 9, B, track)
     if allf:   # give the extra fields targets at the peaks
@@ -176,10 +180,47 @@ def test_backward_vs_autograd(cuda, profile, track, allf):
     yp64 = torch.from_numpy(yp).double().requires_grad_(True)
     ref = _torch_loss64(Lo, torch.from_numpy(yt).double(), yp64)
     (ref * 3.0).backward()
-    assert float(out) == pytest.approx(float(ref), rel=RTOL)
+    assert float(out.detach()) == pytest.approx(float(ref.detach()), rel=RTOL)
     g, gr = yp_d.grad.cpu().double(), yp64.grad
     scale = gr.abs().max()
     assert torch.allclose(g, gr, rtol=1e-4, atol=float(scale) * 1e-6)
+
+
+def test_backward_full_size_fast_equals_generic(cuda, monkeypatch):
+    """BASELINE configs[1] shape (B = 16): the pipelined backward kernel (compile-time layout) against the generic one on the
+    same inputs, and two size-independent properties: the gradient is linear in the upstream gradient and it is zero
+    wherever y_pred has no loss term (regression channels of non-peak pixels)."""
+    import bench
+    from cvmhot import ops
+    from cvmhot.layout import layout_from_params
+    from cvmhot.models.centernet import CenternetParams
+    H, W, K, B = 128, 384, 10, 16
+    p = CenternetParams(K, True)
+    p.INPUT_HEIGHT, p.INPUT_WIDTH = H * p.R, W * p.R
+    L = layout_from_params(p)
+    Lo = make_layout(H, W, K, "N")
+    boxes, cls, ign = bench.gen_objects(3, B)
+    yt = np.stack([render_np.render_image(Lo, boxes[b], cls[b], ign[b]) for b in range(B)])
+    g = torch.Generator(device=cuda).manual_seed(5)
+    yt_d = torch.from_numpy(yt).to(cuda)
+    yp_d = torch.empty((B, H, W, Lo.Cp), device=cuda)
+    yp_d[..., :K] = torch.sigmoid(torch.randn((B, H, W, K), device=cuda, generator=g) * 2.5 - 2.0)   # some outside [.01,.99]
+    yp_d[..., K:] = torch.rand((B, H, W, Lo.Cp - K), device=cuda, generator=g) * 40
+    part = ops.loss_partials(L, yt_d, yp_d, True).clone()
+    fast = ops.loss_backward(L, yt_d, yp_d, part).clone()
+    monkeypatch.setenv("CVM_LOSS_BWD_GENERIC", "1")
+    generic = ops.loss_backward(L, yt_d, yp_d, part).clone()
+    monkeypatch.delenv("CVM_LOSS_BWD_GENERIC")
+    assert torch.isfinite(fast).all()
+    scale = float(generic.abs().max())
+    assert torch.allclose(fast, generic, rtol=1e-5, atol=scale * 1e-7)
+    up = torch.tensor(2.0, device=cuda)
+    twice = ops.loss_backward(L, yt_d, yp_d, part, upstream=up)
+    assert torch.allclose(twice, 2.0 * fast, rtol=1e-6, atol=0)
+    peak = (yt_d[..., :K] == 1.0).any(-1)
+    assert int(peak.sum()) > 0
+    assert float(fast[..., K:][~peak].abs().max()) == 0.0
+    assert float(fast[..., K:][peak].abs().max()) > 0.0
 
 
 def test_loss_properties_full_size(cuda):

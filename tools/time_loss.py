@@ -31,3 +31,14 @@ for i in range(n): ops.loss_partials(L, y_true if i % 2 else yt2, yp if i % 2 el
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
 print(f"{os.environ.get('CVM_TAG', ''):12s} {ms:.4f} ms  {(y_true.numel() + yp.numel()) * 4 / ms / 1e6:.0f} GB/s  loss partial[1]={float(part[1]):.6f}", flush=True)
+
+# backward (d total / d y_pred): reads y_true + y_pred, writes grad
+grad = torch.empty_like(yp)
+for _ in range(3): ops.loss_backward(L, y_true, yp, part, out=grad)
+torch.cuda.synchronize()
+for _ in range(30): _queue.fill_(1.0)
+e0.record()
+for i in range(n): ops.loss_backward(L, y_true if i % 2 else yt2, yp if i % 2 else yp2, part, out=grad)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / n
+print(f"backward     {ms:.4f} ms  {(y_true.numel() + 2 * yp.numel()) * 4 / ms / 1e6:.0f} GB/s", flush=True)
