@@ -62,6 +62,7 @@ struct DecodeParams {
     int* counts;                  // [grid][max_segs]
     unsigned int thr0_bits;       // initial threshold score bits (1 = smallest positive float; experiments only raise it)
     float inv_W;                  // 1 / W
+    int rescan_step;              // appends after which the score histogram is scanned again (test_hits)
 };
 
 // Fixed-size head of the dynamic shared memory block; the ring, the candidate buffer, the select scratch and the score
@@ -118,6 +119,29 @@ size_t smem_bytes(int S, int gran_floats, int cap, int K) {
 #define DBG_STATE(code) do { if ((threadIdx.x & 31) == 0) ((volatile int*)sm_head_raw())[threadIdx.x >> 5] = (code); } while (0)
 #else
 #define DBG_STATE(code) do { } while (0)
+#endif
+
+// -DCVM_DECODE_STATS: per-warp cycle / event counters for tuning (tools/decode_stats.py); never in the shipped build
+#ifdef CVM_DECODE_STATS
+__device__ unsigned long long g_decode_stats[16];
+#define STAT_DECL long long st_t0 = 0; unsigned long long st_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define STAT_BEGIN() (st_t0 = clock64())
+#define STAT_END(i) (st_acc[i] += (unsigned long long)(clock64() - st_t0))
+#define STAT_ADD(i, v) (st_acc[i] += (unsigned long long)(v))
+#define STAT_FLUSH() do { if ((threadIdx.x & 31) == 0) { for (int k_ = 0; k_ < 8; ++k_) atomicAdd(&g_decode_stats[k_], st_acc[k_]); } } while (0)
+#else
+#define STAT_DECL
+#define STAT_BEGIN() ((void)0)
+#define STAT_END(i) ((void)0)
+#define STAT_ADD(i, v) ((void)0)
+#define STAT_FLUSH() ((void)0)
+#endif
+#ifdef CVM_DECODE_STATS
+#define TH_MARK(i) do { const long long t_ = clock64(); if ((threadIdx.x & 31) == 0) atomicAdd(&g_decode_stats[i], (unsigned long long)(t_ - th_t)); th_t = clock64(); } while (0)
+#define TH_START() long long th_t = clock64()
+#else
+#define TH_MARK(i) ((void)0)
+#define TH_START() ((void)0)
 #endif
 
 // named barrier over the first `nt` threads of the CTA (the scanner warps; the loader warp never joins)
@@ -198,9 +222,15 @@ __device__ __noinline__ void select_topk(unsigned long long* keys, int n, int K,
 // becomes the new threshold.  Counts read while other warps append are at worst too low, which only makes the bound
 // conservative.  No buffer traffic, no CTA-wide sync.
 __device__ __noinline__ void scan_threshold(SharedHead* h, const unsigned int* shist, int K, int lane) {
-    const int n = *(volatile const int*)&h->count;
-    if (n == h->scanned || n < K) return;
-    const int top = *(volatile const int*)&h->maxbin;
+    int n = 0, top = 0;
+    if (lane == 0) {   // one lane decides (the words change under our feet), the warp follows
+        n = *(volatile const int*)&h->count;
+        top = *(volatile const int*)&h->maxbin;
+        if (n == *(volatile const int*)&h->scanned || n < K) n = -1;
+    }
+    n = __shfl_sync(0xffffffffu, n, 0);
+    top = __shfl_sync(0xffffffffu, top, 0);
+    if (n < 0) return;
     unsigned above = 0;
     for (int base = top; base >= 0; base -= 32) {
         const int bin = base - lane;
@@ -215,8 +245,7 @@ __device__ __noinline__ void scan_threshold(SharedHead* h, const unsigned int* s
         if (hit) {
             const int tb = base - (__ffs(hit) - 1);
             if (lane == 0) {
-                const unsigned bits = (unsigned)tb << kScoreShift;
-                if (bits > h->thr_bits) h->thr_bits = bits;
+                atomicMax(&h->thr_bits, (unsigned)tb << kScoreShift);   // several warps may scan at once
                 h->scanned = n;
             }
             return;
@@ -312,6 +341,7 @@ struct Hit {
     unsigned long long mask;   // heatmap channels whose score reached the threshold (0: no hit)
     int q;                     // pixel index inside the image
     int rp;                    // ring position (in pixels) of the pixel
+    float vmax;                // largest heatmap score of the pixel
 };
 
 // Offsets (in floats) of channel 0 of the eight neighbours of a hit pixel: into the ring (W + 1 pixels of halo are
@@ -381,73 +411,6 @@ __device__ __forceinline__ bool is_peak(const DecodeParams& p, const float* ring
     return m == v;
 }
 
-// Exact 3x3 test of the pending hits of a warp (NH pixels per lane) and append of the peaks.  Called by ALL lanes of the
-// warp (lanes without a hit pass mask 0): the loop runs over the union of the lanes' channel masks, so votes and the
-// aggregated append (one shared atomic per warp and channel) are warp-uniform; the NH pixels of a lane are tested side
-// by side (independent load chains).  img: image of the pixels.
-template <int NH>
-__device__ __forceinline__ void test_hits(const DecodeParams& p, long long img, const Hit (&hit)[NH], float thr_f) {
-    unsigned long long any = 0ull;
-#pragma unroll
-    for (int k = 0; k < NH; ++k) any |= hit[k].mask;
-    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)any);
-    const unsigned hi = p.hm > 32 ? __reduce_or_sync(0xffffffffu, (unsigned)(any >> 32)) : 0u;
-    unsigned long long uni = ((unsigned long long)hi << 32) | lo;
-    if (uni == 0ull) return;
-    SharedHead* h = sm_head();
-    const float* ring = sm_ring();
-    unsigned long long* cand = sm_cand(p);
-    unsigned int* shist = sm_shist(p);
-    const int lane = threadIdx.x & 31;
-    int nb[NH][8];
-    const float* g_px[NH];
-#pragma unroll
-    for (int k = 0; k < NH; ++k) {
-        g_px[k] = p.yp + ((size_t)img * p.HW + (size_t)hit[k].q) * p.stride;
-        if (hit[k].mask) neighbour_offsets(p, hit[k], nb[k]);
-    }
-    while (uni) {
-        const int ch = __ffsll((long long)uni) - 1;
-        uni &= uni - 1;
-        bool peak[NH];
-        float v[NH];
-        unsigned pm[NH], total = 0;
-#pragma unroll
-        for (int k = 0; k < NH; ++k) {
-            v[k] = 0.f;
-            peak[k] = is_peak(p, ring, g_px[k], hit[k], nb[k], ch, thr_f, v[k]);
-        }
-#pragma unroll
-        for (int k = 0; k < NH; ++k) {
-            pm[k] = __ballot_sync(0xffffffffu, peak[k]);
-            total += __popc(pm[k]);
-        }
-        if (total) {
-            unsigned base = 0;
-            if (lane == 0) base = (unsigned)atomicAdd(&h->count, (int)total);
-            base = __shfl_sync(0xffffffffu, base, 0);
-#pragma unroll
-            for (int k = 0; k < NH; ++k) {
-                if (peak[k]) {
-                    const unsigned pos = base + __popc(pm[k] & ((1u << lane) - 1u));
-                    const unsigned bits = __float_as_uint(v[k]);
-                    const unsigned flat = (unsigned)hit[k].q * (unsigned)p.hm + (unsigned)ch;
-                    cand[pos] = ((unsigned long long)bits << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
-                    if (pos >= (unsigned)p.compact_at) *(volatile int*)&h->compact_flag = 1;
-                    const unsigned bin = bits >> kScoreShift;
-                    atomicAdd(&shist[bin], 1u);
-                    if ((int)bin > *(volatile int*)&h->maxbin) atomicMax(&h->maxbin, (int)bin);
-                }
-                base += __popc(pm[k]);
-            }
-            // Safe point after every batch of appends: once the buffer has passed its mark, a warp adds at most these
-            // <= 32 * NH keys before it joins the compaction, which bounds the buffer (see plan_decode).
-            __syncwarp();
-            if (__any_sync(0xffffffffu, load_ctrl(h).y != 0)) gather(p, false, 0);
-        }
-    }
-}
-
 // bits of the heatmap channels of one pixel whose score reaches the threshold (called for the few pixels whose maximum does)
 template <int HM>
 __device__ __forceinline__ unsigned long long channel_mask(const float* px, int hm, float thr_f) {
@@ -462,6 +425,116 @@ __device__ __forceinline__ unsigned long long channel_mask(const float* px, int 
             if (px[c] >= thr_f) m |= 1ull << c;
     }
     return m;
+}
+
+// Exact 3x3 test of the pending hits of a warp (NH pixels per lane) and append of the peaks.  Called by ALL lanes of the
+// warp (lanes without a hit pass mask 0).  Every round each pixel tests ONE of its pending channels (the channels differ
+// between lanes, the control flow does not: the loop condition is a vote, the ballots and the aggregated append - one
+// shared atomic per warp and round - are warp-uniform); the NH pixels of a lane are tested side by side (independent load
+// chains).  While the segment has no threshold yet (`thr_f` is the initial one) the first round takes each pixel's
+// LARGEST channel: the first K peaks found that way are high ones, and the threshold they give prunes most of the rest.
+// The warp that pushes the count K / 4 past the last histogram scan rescans, and the pending channels are re-filtered
+// whenever the threshold has moved.  img: image of the pixels; thr_f: in/out, the warp's current threshold.
+template <int HM, int NH>
+__device__ __forceinline__ int test_hits(const DecodeParams& p, long long img, const Hit (&hit)[NH], float& thr_f) {
+    unsigned long long rem[NH], any = 0ull;
+#pragma unroll
+    for (int k = 0; k < NH; ++k) {
+        rem[k] = hit[k].mask;
+        any |= rem[k];
+    }
+    if (!__any_sync(0xffffffffu, any != 0ull)) return 0;
+    TH_START();
+    SharedHead* h = sm_head();
+    const float* ring = sm_ring();
+    unsigned long long* cand = sm_cand(p);
+    unsigned int* shist = sm_shist(p);
+    const int lane = threadIdx.x & 31;
+    int nb[NH][8];
+    const float* g_px[NH];
+    unsigned long long pref[NH];
+    int rounds = 0;
+    const bool young = __float_as_uint(thr_f) == p.thr0_bits;
+#pragma unroll
+    for (int k = 0; k < NH; ++k) {
+        g_px[k] = p.yp + ((size_t)img * p.HW + (size_t)hit[k].q) * p.stride;
+        pref[k] = 0ull;
+        if (hit[k].mask) {
+            neighbour_offsets(p, hit[k], nb[k]);
+            if (young) {
+                const unsigned long long top = channel_mask<HM>(ring + (size_t)hit[k].rp * p.stride, p.hm, hit[k].vmax) & hit[k].mask;
+                pref[k] = top & (0ull - top);
+            }
+        }
+    }
+    TH_MARK(12);
+    TH_MARK(9);
+    do {
+        bool peak[NH];
+        float v[NH];
+        int ch[NH];
+        unsigned pm[NH], total = 0;
+#pragma unroll
+        for (int k = 0; k < NH; ++k) {
+            v[k] = 0.f;
+            const unsigned long long sel = pref[k] ? pref[k] : (rem[k] & (0ull - rem[k]));
+            pref[k] = 0ull;
+            ch[k] = sel ? __ffsll((long long)sel) - 1 : 0;
+            peak[k] = sel != 0ull && is_peak(p, ring, g_px[k], hit[k], nb[k], ch[k], thr_f, v[k]);
+            rem[k] &= ~sel;
+        }
+#pragma unroll
+        for (int k = 0; k < NH; ++k) {
+            pm[k] = __ballot_sync(0xffffffffu, peak[k]);
+            total += __popc(pm[k]);
+        }
+        TH_MARK(13);
+        if (total) {
+            unsigned base = 0;
+            int rescan = 0;
+            if (lane == 0) {
+                base = (unsigned)atomicAdd(&h->count, (int)total);
+                const int cnt = (int)(base + total);
+                rescan = cnt >= p.K && cnt - *(volatile int*)&h->scanned >= p.rescan_step;
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            rescan = __shfl_sync(0xffffffffu, rescan, 0);
+#pragma unroll
+            for (int k = 0; k < NH; ++k) {
+                if (peak[k]) {
+                    const unsigned pos = base + __popc(pm[k] & ((1u << lane) - 1u));
+                    const unsigned bits = __float_as_uint(v[k]);
+                    const unsigned flat = (unsigned)hit[k].q * (unsigned)p.hm + (unsigned)ch[k];
+                    cand[pos] = ((unsigned long long)bits << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
+                    if (pos >= (unsigned)p.compact_at) *(volatile int*)&h->compact_flag = 1;
+                    const unsigned bin = bits >> kScoreShift;
+                    atomicAdd(&shist[bin], 1u);
+                    if ((int)bin > *(volatile int*)&h->maxbin) atomicMax(&h->maxbin, (int)bin);
+                }
+                base += __popc(pm[k]);
+            }
+            // Safe point after every batch of appends: once the buffer has passed its mark, a warp adds at most these
+            // <= 32 * NH keys before it joins the compaction, which bounds the buffer (see plan_decode).
+            __syncwarp();
+            if (__any_sync(0xffffffffu, load_ctrl(h).y != 0)) gather(p, false, 0);
+            else if (rescan) scan_threshold(h, shist, p.K, lane);
+        }
+        TH_MARK(14);
+        // the threshold may have moved (our rescan, another warp's, a compaction): drop the pending channels below it
+        const unsigned now_bits = __shfl_sync(0xffffffffu, load_ctrl(h).x, 0);
+        if (now_bits > __float_as_uint(thr_f)) {
+            thr_f = __uint_as_float(now_bits);
+#pragma unroll
+            for (int k = 0; k < NH; ++k)
+                if (rem[k]) rem[k] &= channel_mask<HM>(ring + (size_t)hit[k].rp * p.stride, p.hm, thr_f);
+        }
+        any = 0ull;
+#pragma unroll
+        for (int k = 0; k < NH; ++k) any |= rem[k];
+        ++rounds;
+        TH_MARK(15);
+    } while (__any_sync(0xffffffffu, any != 0ull));
+    return rounds;   // statistics only
 }
 
 // maximum over the HM leading floats of one pixel; STRIDE > 0: compile-time layout, widest aligned vector loads
@@ -498,6 +571,19 @@ __device__ __forceinline__ float pixel_max(const float* px, int hm) {
 // all of them, then everybody takes the same decisions from state that cannot change while all are paused.
 __device__ __noinline__ void gather(const DecodeParams& p, bool at_segment_end, int seg) {
     SharedHead* h = sm_head();
+#ifdef CVM_DECODE_STATS
+    const long long g_t0 = clock64();
+    struct GatherTimer {
+        long long t0;
+        bool seg;
+        __device__ ~GatherTimer() {
+            if ((threadIdx.x & 31) == 0) {
+                atomicAdd(&g_decode_stats[seg ? 10 : 8], (unsigned long long)(clock64() - t0));
+                atomicAdd(&g_decode_stats[seg ? 11 : 9], 1ull);
+            }
+        }
+    } g_timer{g_t0, at_segment_end};
+#endif
     for (;;) {
         DBG_STATE(at_segment_end ? 21 : 20);
         group_sync(kScanThreads);   // everybody paused: no appends in flight
@@ -658,6 +744,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
     z.waited = z.w_slot = z.released = z.r_slot = 0;
     z.w_parity = 0u;
 
+    STAT_DECL;
     long long img = img0;
     int st = st0;
     int gseq = lead;         // sequence number of the first granule of the current step
@@ -670,7 +757,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
         // this step's granules and their lookahead (W + 1 pixels past the end of the step): a pixel is scanned and, if it
         // reaches the threshold, tested in the same step
         DBG_STATE(100 + i * 1000);
+        STAT_BEGIN();
         wait_until(p, z, min(gseq + gc - 1 + hg, seq_last) + 1);
+        STAT_END(0);
+        STAT_BEGIN();
         DBG_STATE(101 + i * 1000);
         Hit cur[GPS];
 #pragma unroll
@@ -683,11 +773,28 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
             cur[k].rp = sl * T + tid;   // ring position of this lane's pixel
             if (k < gc && tid < min(T, HW - q0)) {
                 const float* px = ring + (size_t)cur[k].rp * stride;
-                if (pixel_max<STRIDE, HM>(px, p.hm) >= z.thr_f) cur[k].mask = channel_mask<HM>(px, p.hm, z.thr_f);
+                cur[k].vmax = pixel_max<STRIDE, HM>(px, p.hm);
+                if (cur[k].vmax >= z.thr_f) cur[k].mask = channel_mask<HM>(px, p.hm, z.thr_f);
             }
         }
         DBG_STATE(102 + i * 1000);
-        test_hits<GPS>(p, img, cur, z.thr_f);
+        STAT_END(1);
+#ifdef CVM_DECODE_STATS
+        for (int k = 0; k < GPS; ++k) {
+            STAT_ADD(4, __popc(__ballot_sync(0xffffffffu, cur[k].mask != 0ull)));                 // pixel hits
+        }
+        STAT_ADD(6, 1);                                                                          // warp-steps
+#endif
+        STAT_BEGIN();
+#ifdef CVM_DECODE_STATS
+        const bool was_young = __float_as_uint(z.thr_f) == p.thr0_bits;
+        const int n_rounds = test_hits<HM, GPS>(p, img, cur, z.thr_f);
+        STAT_ADD(5, n_rounds);
+        if (was_young) { STAT_END(7); } else { STAT_END(2); }
+#else
+        test_hits<HM, GPS>(p, img, cur, z.thr_f);
+#endif
+        STAT_BEGIN();
         const bool segment_end = (st + 1 == spi) || (i + 1 == n_local);
         const bool image_end = st + 1 == spi;
         // the next step needs halo_g granules of history before its first granule: the rest is dead
@@ -715,7 +822,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
         gseq += gc;
         cur_slot += gc;
         if (cur_slot >= S) cur_slot -= S;
+        STAT_END(3);
     }
+    STAT_FLUSH();
 }
 
 struct MergeParams {
@@ -998,6 +1107,7 @@ extern "C" int cvm_decode_topk(const cvm_layout* L, const float* y_pred, int pre
     p.counts = reinterpret_cast<int*>(static_cast<unsigned char*>(ws) + t.ws_keys);
     p.thr0_bits = 1u;
     p.inv_W = 1.0f / (float)L->W;
+    p.rescan_step = env_int("CVM_DECODE_RESCAN", K / 4 > 8 ? K / 4 : 8);
     if (const char* e = getenv("CVM_DECODE_THR0")) {   // experiment knob (results are wrong when set): start threshold
         const float f = (float)atof(e);
         memcpy(&p.thr0_bits, &f, 4);
@@ -1043,3 +1153,15 @@ extern "C" int cvm_decode_topk(const cvm_layout* L, const float* y_pred, int pre
     CVM_CHECK_LAUNCH("decode_merge_kernel");
     return CVM_OK;
 }
+
+#ifdef CVM_DECODE_STATS
+extern "C" int cvm_decode_stats(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, g_decode_stats, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_decode_stats, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
