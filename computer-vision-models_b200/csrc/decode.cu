@@ -24,6 +24,8 @@
 #include <limits.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -36,7 +38,10 @@ constexpr int kMergeThreads = 256;
 constexpr int kMaxSlots = 32;      // ring depth (granules) the barrier arrays can hold
 constexpr int kSlack = 1536;       // buffer entries beyond K before the (rare) fallback compaction
 constexpr int kSegKeys = 512;      // keys a segment may publish without an exact select (the merge kernel selects anyway)
-constexpr int kScoreShift = 19;    // score histogram: bin = float bits >> 19 (sign 0, 8 exponent bits, 4 mantissa bits)
+#ifndef CVM_SCORE_SHIFT
+#define CVM_SCORE_SHIFT 19
+#endif
+constexpr int kScoreShift = CVM_SCORE_SHIFT;    // score histogram: bin = float bits >> 19 (sign 0, 8 exponent bits, 4 mantissa bits)
 constexpr int kScoreBins = 1 << (31 - kScoreShift);
 constexpr int kMaxK = 1024;
 constexpr int kMergeCap = 4096;    // merge kernel: keys buffered before an intermediate select
@@ -337,8 +342,15 @@ __device__ __forceinline__ uint2 load_ctrl(const SharedHead* h) {
 }
 
 // One lane's pixel that reached the threshold and waits for its 3x3 test.
+// channel masks: 32 bits when the compile-time channel count allows it (registers are tight in the scan kernel)
+template <int HM>
+using mask_t = typename std::conditional<(HM > 0 && HM <= 32), unsigned int, unsigned long long>::type;
+template <typename M>
+__device__ __forceinline__ int lowest_bit(M m) { return sizeof(M) == 4 ? __ffs((int)m) - 1 : __ffsll((long long)m) - 1; }
+
+template <int HM>
 struct Hit {
-    unsigned long long mask;   // heatmap channels whose score reached the threshold (0: no hit)
+    mask_t<HM> mask;           // heatmap channels whose score reached the threshold (0: no hit)
     int q;                     // pixel index inside the image
     int rp;                    // ring position (in pixels) of the pixel
     float vmax;                // largest heatmap score of the pixel
@@ -347,7 +359,8 @@ struct Hit {
 // Offsets (in floats) of channel 0 of the eight neighbours of a hit pixel: into the ring (W + 1 pixels of halo are
 // resident) or relative to the pixel in global memory; INT_MIN outside the map.  Interior pixels whose neighbourhood does
 // not wrap around the ring (almost all) take the short way.
-__device__ __forceinline__ void neighbour_offsets(const DecodeParams& p, const Hit& hit, int (&nb)[8]) {
+template <int HM>
+__device__ __forceinline__ void neighbour_offsets(const DecodeParams& p, const Hit<HM>& hit, int (&nb)[8]) {
     const int W = p.W, stride = p.stride, ring_px = p.S * p.T;
     // y = q / W without an integer division (exact after one correction step for any q < 2^31)
     const int q = hit.q;
@@ -393,9 +406,9 @@ __device__ __forceinline__ void neighbour_offsets(const DecodeParams& p, const H
 
 // is channel ch of the hit pixel a peak (its value equals its 3x3 maximum; plateaus are all kept) that still reaches the
 // threshold (it may have risen since the scan; it is > 0, so score-0 entries never get here)?
-__device__ __forceinline__ bool is_peak(const DecodeParams& p, const float* ring, const float* g_px, const Hit& hit,
+template <int HM>
+__device__ __forceinline__ bool is_peak(const DecodeParams& p, const float* ring, const float* g_px, const Hit<HM>& hit,
                                         const int (&nb)[8], int ch, float thr_f, float& v) {
-    if (!((hit.mask >> ch) & 1ull)) return false;
     v = ring[hit.rp * p.stride + ch];
     if (!(v >= thr_f)) return false;
     float m = v;
@@ -413,8 +426,8 @@ __device__ __forceinline__ bool is_peak(const DecodeParams& p, const float* ring
 
 // bits of the heatmap channels of one pixel whose score reaches the threshold (called for the few pixels whose maximum does)
 template <int HM>
-__device__ __forceinline__ unsigned long long channel_mask(const float* px, int hm, float thr_f) {
-    unsigned long long m = 0ull;
+__device__ __forceinline__ mask_t<HM> channel_mask(const float* px, int hm, float thr_f) {
+    mask_t<HM> m = 0;
     if (HM > 0) {
         unsigned lo = 0u;   // HM <= 32 in every instantiation
 #pragma unroll
@@ -422,7 +435,7 @@ __device__ __forceinline__ unsigned long long channel_mask(const float* px, int 
         m = lo;
     } else {
         for (int c = 0; c < hm; ++c)
-            if (px[c] >= thr_f) m |= 1ull << c;
+            if (px[c] >= thr_f) m |= (mask_t<HM>)1 << c;
     }
     return m;
 }
@@ -436,14 +449,15 @@ __device__ __forceinline__ unsigned long long channel_mask(const float* px, int 
 // The warp that pushes the count K / 4 past the last histogram scan rescans, and the pending channels are re-filtered
 // whenever the threshold has moved.  img: image of the pixels; thr_f: in/out, the warp's current threshold.
 template <int HM, int NH>
-__device__ __forceinline__ int test_hits(const DecodeParams& p, long long img, const Hit (&hit)[NH], float& thr_f) {
-    unsigned long long rem[NH], any = 0ull;
+__device__ __forceinline__ int test_hits(const DecodeParams& p, long long img, const Hit<HM> (&hit)[NH], float& thr_f) {
+    using M = mask_t<HM>;
+    M rem[NH], any = 0;
 #pragma unroll
     for (int k = 0; k < NH; ++k) {
         rem[k] = hit[k].mask;
         any |= rem[k];
     }
-    if (!__any_sync(0xffffffffu, any != 0ull)) return 0;
+    if (!__any_sync(0xffffffffu, any != 0)) return 0;
     TH_START();
     SharedHead* h = sm_head();
     const float* ring = sm_ring();
@@ -452,18 +466,18 @@ __device__ __forceinline__ int test_hits(const DecodeParams& p, long long img, c
     const int lane = threadIdx.x & 31;
     int nb[NH][8];
     const float* g_px[NH];
-    unsigned long long pref[NH];
+    M pref[NH];
     int rounds = 0;
     const bool young = __float_as_uint(thr_f) == p.thr0_bits;
 #pragma unroll
     for (int k = 0; k < NH; ++k) {
         g_px[k] = p.yp + ((size_t)img * p.HW + (size_t)hit[k].q) * p.stride;
-        pref[k] = 0ull;
+        pref[k] = 0;
         if (hit[k].mask) {
             neighbour_offsets(p, hit[k], nb[k]);
             if (young) {
-                const unsigned long long top = channel_mask<HM>(ring + (size_t)hit[k].rp * p.stride, p.hm, hit[k].vmax) & hit[k].mask;
-                pref[k] = top & (0ull - top);
+                const M top = channel_mask<HM>(ring + (size_t)hit[k].rp * p.stride, p.hm, hit[k].vmax) & hit[k].mask;
+                pref[k] = top & ((M)0 - top);
             }
         }
     }
@@ -477,10 +491,10 @@ __device__ __forceinline__ int test_hits(const DecodeParams& p, long long img, c
 #pragma unroll
         for (int k = 0; k < NH; ++k) {
             v[k] = 0.f;
-            const unsigned long long sel = pref[k] ? pref[k] : (rem[k] & (0ull - rem[k]));
-            pref[k] = 0ull;
-            ch[k] = sel ? __ffsll((long long)sel) - 1 : 0;
-            peak[k] = sel != 0ull && is_peak(p, ring, g_px[k], hit[k], nb[k], ch[k], thr_f, v[k]);
+            const M sel = pref[k] ? pref[k] : (rem[k] & ((M)0 - rem[k]));
+            pref[k] = 0;
+            ch[k] = sel ? lowest_bit(sel) : 0;
+            peak[k] = sel != 0 && is_peak(p, ring, g_px[k], hit[k], nb[k], ch[k], thr_f, v[k]);
             rem[k] &= ~sel;
         }
 #pragma unroll
@@ -528,12 +542,12 @@ __device__ __forceinline__ int test_hits(const DecodeParams& p, long long img, c
             for (int k = 0; k < NH; ++k)
                 if (rem[k]) rem[k] &= channel_mask<HM>(ring + (size_t)hit[k].rp * p.stride, p.hm, thr_f);
         }
-        any = 0ull;
+        any = 0;
 #pragma unroll
         for (int k = 0; k < NH; ++k) any |= rem[k];
         ++rounds;
         TH_MARK(15);
-    } while (__any_sync(0xffffffffu, any != 0ull));
+    } while (__any_sync(0xffffffffu, any != 0));
     return rounds;   // statistics only
 }
 
@@ -762,13 +776,13 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
         STAT_END(0);
         STAT_BEGIN();
         DBG_STATE(101 + i * 1000);
-        Hit cur[GPS];
+        Hit<HM> cur[GPS];
 #pragma unroll
         for (int k = 0; k < GPS; ++k) {
             int sl = cur_slot + k;
             if (sl >= S) sl -= S;
             const int q0 = (g0 + k) * T;
-            cur[k].mask = 0ull;
+            cur[k].mask = 0;
             cur[k].q = q0 + tid;
             cur[k].rp = sl * T + tid;   // ring position of this lane's pixel
             if (k < gc && tid < min(T, HW - q0)) {
@@ -781,7 +795,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
         STAT_END(1);
 #ifdef CVM_DECODE_STATS
         for (int k = 0; k < GPS; ++k) {
-            STAT_ADD(4, __popc(__ballot_sync(0xffffffffu, cur[k].mask != 0ull)));                 // pixel hits
+            STAT_ADD(4, __popc(__ballot_sync(0xffffffffu, cur[k].mask != 0)));                 // pixel hits
         }
         STAT_ADD(6, 1);                                                                          // warp-steps
 #endif
@@ -974,9 +988,10 @@ int plan_decode(const cvm_layout* L, int stride, int B, int K, Plan* t) {
     const long long HW = (long long)L->H * W;
     // granule: one pixel per scanner thread, fewer when the image is smaller; a step is 2 granules when the ring has room
     // (the per-step bookkeeping and the latency of the hit tests are then paid once per 2 pixels of every lane)
-    int T = kScanThreads;
+    int T = env_int("CVM_DECODE_T", kScanThreads);
+    if (T > kScanThreads || T < 32 || T % 32) T = kScanThreads;
     if (HW < T) T = (int)((HW + 31) / 32 * 32);
-    t->compact_at = K + kSlack;
+    t->compact_at = K + env_int("CVM_DECODE_SLACK", kSlack);
     t->cap = t->compact_at + 1 + 2 * kScanThreads;   // every warp stops within 32 appends per pixel of a lane of the mark (test_hits)
     const size_t fixed = smem_bytes(0, 0, t->cap, K);
     int gps_want = env_int("CVM_DECODE_GPS", 2);
