@@ -25,11 +25,7 @@ constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxObjSmem = 64;   // objects are processed in batches of this many
 constexpr int kMaxIgnSmem = 16;     // ignore boxes cached in shared memory per image (more are read from global)
-#ifndef CVM_RENDER_BUFFERS
-#define CVM_RENDER_BUFFERS 1
-#endif
-constexpr int kBuffers = CVM_RENDER_BUFFERS;   // staging buffers per CTA (two CTAs per SM: one builds while the other's chunk streams out)
-constexpr int kChunkBytes = 86016 / kBuffers;
+constexpr int kChunkBytes = 86016;   // staging buffer per CTA (two CTAs per SM: one builds while the other's chunk streams out)
 constexpr int kMaxUnits = 512;       // (object, 32-column segment) work units per chunk and object batch
 constexpr int kColTab = 1024;        // entries of the per-image column-factor table (objects that do not fit use exp)
 constexpr int kRowTab = 1024;        // entries of the per-image row-factor table
@@ -127,7 +123,7 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-extern __shared__ __align__(128) unsigned char g_render_smem[];   // kBuffers staging buffers of kChunkBytes
+extern __shared__ __align__(128) unsigned char g_render_smem[];   // the staging buffer (kChunkBytes)
 
 // max / min combine of a float into shared memory through integer atomics on the bit pattern: non-negative floats order
 // like signed ints, negative floats order inversely like unsigned ints, and each of the two operations keeps the cell
@@ -191,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
         const int q0 = ci * P, q1 = min(HW, q0 + P), npx = q1 - q0;
         int yb = ya;   // row of the chunk's last pixel
         for (int t = xa + npx - 1; t >= W; t -= W) ++yb;
-        float* const st = stage0 + (size_t)(kBuffers > 1 ? (it & 1) : 0) * (kChunkBytes / 4);
+        float* const st = stage0;
         const bool new_img = loaded_img != img;
         if (new_img) {   // object / ignore-box ranges of the image: fetched once per image, not once per chunk
             o_begin = p.obj_offsets[img];
@@ -204,12 +200,6 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
             }
         }
 
-        // ---- phase 1: pattern fill (heat = 0, weights = 1, regression targets = 0; processor.py:267-268) ----
-        if (tid < n_fill && !(p.dbg_skip & 4)) {
-            const int n4 = (npx * Cout + 3) >> 2;   // the buffer is a whole number of float4s
-            float4* s4 = reinterpret_cast<float4*>(st);
-            for (int f = tid; f < n4; f += n_fill) s4[f] = fill_v;
-        }
         if (new_img) {   // clamp the ignore boxes once per image (read after the barriers below)
             if (tid < min(n_ign, kMaxIgnSmem)) {
                 const cvm_box bx = p.ignore[i_begin + tid];
@@ -220,92 +210,111 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
             }
         }
 
-        for (int bi = 0; bi < n_batches; ++bi) {   // one batch in the common case
+
+        // The pre-work of a chunk - per-image tables and the chunk's work units, nothing that touches the staging buffer -
+        // runs BEFORE the wait for the buffer, i.e. while the bulk store of the previous chunk is still reading it (every
+        // reader of these arrays finished before barrier B of the previous chunk).  Batches after the first one of a
+        // crowded image (rare) do the same work inline.
+        for (int bi = 0;; ++bi) {
+            const bool have = bi < n_batches;
             const int base = o_begin + bi * kMaxObjSmem;
-            const int n = min(kMaxObjSmem, o_end - base);
-            const int par = (lk++) & 1;
-            if (new_img || loaded_base != base) {
-                // ---- once per image (and object batch): derived records, scatter winners, column factors ----
-                if (bi > 0) __syncthreads();   // the previous batch is still being read
-                if (tid < n) derive(p.objs[base + tid], p, sobj[tid]);
-                __syncthreads();
-                if (tid < n && scatter) {
-                    // a later object (list order) on the same centre pixel overwrites r_offset / fullbox / track_offset
-                    // (processor.py:288-299), so only the last one writes them
-                    const int sx = sobj[tid].scx, sy = sobj[tid].scy;
-                    bool last = true;
-                    for (int j = base + tid + 1; j < o_end && last; ++j) {
-                        if (j - base < n) {
-                            if (sobj[j - base].scx == sx && sobj[j - base].scy == sy) last = false;
-                        } else {
-                            ObjDerived e;
-                            derive(p.objs[j], p, e);
-                            if (e.scx == sx && e.scy == sy) last = false;
+            const int n = have ? min(kMaxObjSmem, o_end - base) : 0;
+            const int par = have ? (lk++) & 1 : 0;
+            if (have) {
+                if (new_img || loaded_base != base) {
+                    // ---- once per image (and object batch): derived records, scatter winners, column factors ----
+                    if (bi > 0) __syncthreads();   // the previous batch is still being read
+                    if (tid < n) derive(p.objs[base + tid], p, sobj[tid]);
+                    __syncthreads();
+                    if (tid < n && scatter) {
+                        // a later object (list order) on the same centre pixel overwrites r_offset / fullbox / track_offset
+                        // (processor.py:288-299), so only the last one writes them
+                        const int sx = sobj[tid].scx, sy = sobj[tid].scy;
+                        bool last = true;
+                        for (int j = base + tid + 1; j < o_end && last; ++j) {
+                            if (j - base < n) {
+                                if (sobj[j - base].scx == sx && sobj[j - base].scy == sy) last = false;
+                            } else {
+                                ObjDerived e;
+                                derive(p.objs[j], p, e);
+                                if (e.scx == sx && e.scy == sy) last = false;
+                            }
                         }
+                        sobj[tid].last_at_pixel = last;
                     }
-                    sobj[tid].last_at_pixel = last;
-                }
-                if (tid < n) {   // table space in object order; an object that does not fit evaluates exp per pixel
-                    int off = 0, offr = 0;
-                    for (int o = 0; o < tid; ++o) {
-                        off += max(0, sobj[o].x1 - sobj[o].x0);
-                        offr += max(0, sobj[o].y1 - sobj[o].y0);
-                    }
-                    const int wd = max(0, sobj[tid].x1 - sobj[tid].x0), ht = max(0, sobj[tid].y1 - sobj[tid].y0);
-                    const int tab = off + wd <= kColTab ? off : -1, tabr = offr + ht <= kRowTab ? offr : -1;
-                    // owner of every table entry, so that the factors can be computed one entry per thread
-                    if (tab >= 0)
-                        for (int k = 0; k < wd; ++k) s_own[tab + k] = (unsigned char)tid;
-                    if (tabr >= 0)
-                        for (int k = 0; k < ht; ++k) s_own[kColTab + tabr + k] = (unsigned char)tid;
-                    if (tid == n - 1) {
-                        s_used[0] = tab >= 0 ? tab + wd : 0;      // (the last object fits only if all before it did)
-                        s_used[1] = tabr >= 0 ? tabr + ht : 0;
-                    }
-                    sobj[tid].tab = tab;
-                    sobj[tid].tabr = tabr;
-                }
-                __syncthreads();
-                if (sobj[n - 1].tab < 0 || sobj[n - 1].tabr < 0) {
-                    // some object did not fit: its entries are not tabulated, the entries before it are found by scanning
-                    if (tid == 0) {
-                        int used = 0, usedr = 0;
-                        for (int o = 0; o < n; ++o) {
-                            if (sobj[o].tab >= 0) used = sobj[o].tab + max(0, sobj[o].x1 - sobj[o].x0);
-                            if (sobj[o].tabr >= 0) usedr = sobj[o].tabr + max(0, sobj[o].y1 - sobj[o].y0);
+                    if (tid < n) {   // table space in object order; an object that does not fit evaluates exp per pixel
+                        int off = 0, offr = 0;
+                        for (int o = 0; o < tid; ++o) {
+                            off += max(0, sobj[o].x1 - sobj[o].x0);
+                            offr += max(0, sobj[o].y1 - sobj[o].y0);
                         }
-                        s_used[0] = used;
-                        s_used[1] = usedr;
+                        const int wd = max(0, sobj[tid].x1 - sobj[tid].x0), ht = max(0, sobj[tid].y1 - sobj[tid].y0);
+                        const int tab = off + wd <= kColTab ? off : -1, tabr = offr + ht <= kRowTab ? offr : -1;
+                        // owner of every table entry, so that the factors can be computed one entry per thread
+                        if (tab >= 0)
+                            for (int k = 0; k < wd; ++k) s_own[tab + k] = (unsigned char)tid;
+                        if (tabr >= 0)
+                            for (int k = 0; k < ht; ++k) s_own[kColTab + tabr + k] = (unsigned char)tid;
+                        if (tid == n - 1) {
+                            s_used[0] = tab >= 0 ? tab + wd : 0;      // (the last object fits only if all before it did)
+                            s_used[1] = tabr >= 0 ? tabr + ht : 0;
+                        }
+                        sobj[tid].tab = tab;
+                        sobj[tid].tabr = tabr;
                     }
                     __syncthreads();
-                }
-                {
-                    const int used = s_used[0], usedr = s_used[1];
-                    for (int e = tid; e < used + usedr; e += kThreads) {
-                        if (e < used) {
-                            const ObjDerived& d = sobj[s_own[e]];
-                            const double dx = (double)(d.x0 + (e - d.tab) - d.cx);
-                            s_col[e] = exp(-(dx * dx * d.inv2vx));
-                        } else {
-                            const int r = e - used;
-                            const ObjDerived& d = sobj[s_own[kColTab + r]];
-                            const double dy = (double)(d.y0 + (r - d.tabr) - d.cy);
-                            s_row[r] = exp(-(dy * dy * d.inv2vy));
+                    if (sobj[n - 1].tab < 0 || sobj[n - 1].tabr < 0) {
+                        // some object did not fit: its entries are not tabulated, the entries before it are found by scanning
+                        if (tid == 0) {
+                            int used = 0, usedr = 0;
+                            for (int o = 0; o < n; ++o) {
+                                if (sobj[o].tab >= 0) used = sobj[o].tab + max(0, sobj[o].x1 - sobj[o].x0);
+                                if (sobj[o].tabr >= 0) usedr = sobj[o].tabr + max(0, sobj[o].y1 - sobj[o].y0);
+                            }
+                            s_used[0] = used;
+                            s_used[1] = usedr;
+                        }
+                        __syncthreads();
+                    }
+                    {
+                        const int used = s_used[0], usedr = s_used[1];
+                        for (int e = tid; e < used + usedr; e += kThreads) {
+                            if (e < used) {
+                                const ObjDerived& d = sobj[s_own[e]];
+                                const double dx = (double)(d.x0 + (e - d.tab) - d.cx);
+                                s_col[e] = exp(-(dx * dx * d.inv2vx));
+                            } else {
+                                const int r = e - used;
+                                const ObjDerived& d = sobj[s_own[kColTab + r]];
+                                const double dy = (double)(d.y0 + (r - d.tabr) - d.cy);
+                                s_row[r] = exp(-(dy * dy * d.inv2vy));
+                            }
                         }
                     }
+                    loaded_base = base;
                 }
-                loaded_base = base;
+                // ---- work units of this chunk ----
+                if (tid < n && !(p.dbg_skip & 32)) {
+                    const ObjDerived& d = sobj[tid];
+                    if (max(d.y0, ya) < min(d.y1, yb + 1) && d.x0 < d.x1) {
+                        const int u = (d.x1 - d.x0 + 31) >> 5;
+                        const int start = atomicAdd(&s_nunits[par], u);
+                        for (int k = 0; k < u && start + k < kMaxUnits; ++k) s_unit[start + k] = tid | (k << 8);
+                    }
+                }
+                if (tid == 0) s_nunits[par ^ 1] = 0;   // the other counter is idle: reset it for the next build
             }
-            // ---- work units of this chunk ----
-            if (tid < n && !(p.dbg_skip & 32)) {
-                const ObjDerived& d = sobj[tid];
-                if (max(d.y0, ya) < min(d.y1, yb + 1) && d.x0 < d.x1) {
-                    const int u = (d.x1 - d.x0 + 31) >> 5;
-                    const int start = atomicAdd(&s_nunits[par], u);
-                    for (int k = 0; k < u && start + k < kMaxUnits; ++k) s_unit[start + k] = tid | (k << 8);
+            if (bi == 0) {
+                if (p.bulk && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous chunk has left the buffer
+                __syncthreads();   // ---- barrier C: the buffer is free ----
+                // ---- phase 1: pattern fill (heat = 0, weights = 1, regression targets = 0; processor.py:267-268) ----
+                if (tid < n_fill && !(p.dbg_skip & 4)) {
+                    const int n4 = (npx * Cout + 3) >> 2;   // the buffer is a whole number of float4s
+                    float4* s4 = reinterpret_cast<float4*>(st);
+                    for (int f = tid; f < n4; f += n_fill) s4[f] = fill_v;
                 }
             }
-            if (tid == 0) s_nunits[par ^ 1] = 0;   // the other counter is idle: reset it for the next build
+            if (!have) break;
             __syncthreads();   // ---- barrier A: fill, tables and units are visible ----
 
             // ---- phase 2: one warp per (unit, row) item, lane = column; max/min-combine with shared atomics (windows of
@@ -402,21 +411,9 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
         // ---- stream the chunk out ----
         if (p.bulk) {
             if (!(p.dbg_skip & 16)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk engine
-            if (kBuffers > 1) {
-                // the next chunk refills the other buffer right after the barrier: its bulk store must have finished reading
-                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncthreads();   // ---- barrier B: the chunk is complete ----
-                if (tid == 0 && !(p.dbg_skip & 2)) bulk_s2g(p.out + ((size_t)img * HW + q0) * Cout, st, (uint32_t)(npx * Cout * 4));
-            } else {
-                __syncthreads();   // ---- barrier B: the chunk is complete ----
-                if (tid == 0) {
-                    if (!(p.dbg_skip & 2)) bulk_s2g(p.out + ((size_t)img * HW + q0) * Cout, st, (uint32_t)(npx * Cout * 4));
-                    // the next chunk is built in the same buffer: the bulk engine must have finished reading it (meanwhile
-                    // the SM's other CTA builds its chunk)
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                }
-                __syncthreads();   // ---- barrier C ----
-            }
+            __syncthreads();   // ---- barrier B: the chunk is complete ----
+            // the buffer is rebuilt only after barrier C of the next iteration (meanwhile the SM's other CTA builds its chunk)
+            if (tid == 0 && !(p.dbg_skip & 2)) bulk_s2g(p.out + ((size_t)img * HW + q0) * Cout, st, (uint32_t)(npx * Cout * 4));
         } else {
             __syncthreads();
             float* const dst = p.out + ((size_t)img * HW + q0) * Cout;
@@ -464,7 +461,7 @@ int launch_render(const RenderParams& p0, int B, cudaStream_t st) {
     p.vec = p.bulk;
     if (const char* e = getenv("CVM_RENDER_SKIP")) p.dbg_skip = atoi(e);
     if (p.dbg_skip & 8) p.bulk = 0;   // experiment: plain stores instead of bulk copies
-    const size_t smem = (size_t)kBuffers * kChunkBytes;
+    const size_t smem = (size_t)kChunkBytes;
     CVM_CHECK_CUDA(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = 2LL * cvm_num_sms();
     if (grid > p.n_chunks) grid = p.n_chunks;
