@@ -325,17 +325,22 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
             for (int it = warp; it < n_items; it += kWarps) {
                 const int u = overflow ? it : s_unit[it];
                 const ObjDerived& d = sobj[u & 255];
-                if (d.x0 >= d.x1) continue;
-                int xs = d.x0, xe = d.x1;
+                // the record is read ONCE: the shared atomics below are memory clobbers, anything read through `d` after
+                // them would be reloaded row after row (a chain of dependent shared loads per row)
+                const int x0 = d.x0, x1 = d.x1, y0 = d.y0, tab = d.tab, tabr = d.tabr;
+                const int r0 = max(y0, ya), r1 = min(d.y1, yb + 1);
+                float* const plane_px = st + d.plane;
+                const double peak = d.peak, rw = d.rw;
+                if (x0 >= x1) continue;
+                int xs = x0, xe = x1;
                 if (!overflow) {
-                    xs = d.x0 + ((u >> 8) << 5);
-                    xe = min(d.x1, xs + 32);
+                    xs = x0 + ((u >> 8) << 5);
+                    xe = min(x1, xs + 32);
                 }
-                const int r0 = max(d.y0, ya), r1 = min(d.y1, yb + 1);
                 for (int x = xs + lane; x < xe; x += 32) {
                     double ex;
-                    if (d.tab >= 0) {
-                        ex = s_col[d.tab + (x - d.x0)];
+                    if (tab >= 0) {
+                        ex = s_col[tab + (x - x0)];
                     } else {
                         const double dx = (double)(x - d.cx);
                         ex = exp(-(dx * dx * d.inv2vx));
@@ -344,16 +349,16 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
                         const int q = y * W + x;
                         if (q < q0 || q >= q1) continue;   // the chunk may start / end inside a row
                         double ey;
-                        if (d.tabr >= 0) {
-                            ey = s_row[d.tabr + (y - d.y0)];
+                        if (tabr >= 0) {
+                            ey = s_row[tabr + (y - y0)];
                         } else {
                             const double dy = (double)(y - d.cy);
                             ey = exp(-(dy * dy * d.inv2vy));
                         }
                         const double gv = ex * ey;                                           // processor.py:34-36
-                        float* const px = st + (size_t)(q - q0) * Cout;
-                        smem_max_float(px + d.plane, (float)(gv * d.peak));                   // :37
-                        if (has_w) smem_min_float(px + wch, (float)(1.0 - d.rw * gv));        // :38
+                        const int o = (q - q0) * Cout;
+                        smem_max_float(plane_px + o, (float)(gv * peak));                     // :37
+                        if (has_w) smem_min_float(st + o + wch, (float)(1.0 - rw * gv));      // :38
                     }
                 }
             }
