@@ -7,6 +7,8 @@
 // in scan order (the reference's output order) and assembles class / centre / box.
 //
 // cvm_semseg_argmax replaces to_3channel (reference common/utils/image.py:72-100).
+#include <limits.h>
+
 #include "common.cuh"
 
 namespace {
@@ -284,5 +286,111 @@ extern "C" int cvm_semseg_argmax(const float* in, long long n_pixels, int stride
     const long long gmax = (long long)cvm_num_sms() * 16;
     semseg_argmax_kernel<<<(unsigned)(g < gmax ? g : gmax), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     CVM_CHECK_LAUNCH("semseg_argmax_kernel");
+    return CVM_OK;
+}
+
+// ---- CenterTrack association -------------------------------------------------------------------------
+namespace {
+
+struct AssocParams {
+    const float* centers;
+    const float* track;
+    const float* boxes;
+    const float* scores;
+    const int32_t* cls;
+    const float* prev_centers;
+    const float* prev_sizes;
+    const int32_t* prev_cls;
+    const int32_t* prev_count;
+    int32_t* match;
+    int K, M;
+    float min_score;
+};
+
+// One warp per image.  The greedy loop over the detections is sequential by definition (a match removes a previous track
+// for all later detections); the search over the previous tracks is spread over the lanes and reduced with shuffles.
+// Un-fused fp32 ops, x term + y term: the distances are the ones numpy computes, so ties break identically.
+__global__ void __launch_bounds__(32) track_associate_kernel(const AssocParams p) {
+    extern __shared__ __align__(16) unsigned char assoc_smem[];
+    const int b = blockIdx.x, lane = threadIdx.x, K = p.K, M = p.M;
+    float* pcx = reinterpret_cast<float*>(assoc_smem);
+    float* pcy = pcx + M;
+    float* psz = pcy + M;
+    int* pcl = reinterpret_cast<int*>(psz + M);   // class of the previous track, INT_MIN once it is taken
+    int n_prev = p.prev_count ? p.prev_count[b] : M;
+    n_prev = n_prev < 0 ? 0 : (n_prev > M ? M : n_prev);
+    for (int j = lane; j < n_prev; j += 32) {
+        const size_t o = (size_t)b * M + j;
+        pcx[j] = p.prev_centers[o * 2];
+        pcy[j] = p.prev_centers[o * 2 + 1];
+        psz[j] = __fmul_rn(p.prev_sizes[o * 2], p.prev_sizes[o * 2 + 1]);
+        pcl[j] = p.prev_cls[o];
+    }
+    __syncwarp();
+    for (int i = 0; i < K; ++i) {
+        const size_t o = (size_t)b * K + i;
+        int found = -1;
+        const float s = p.scores[o];
+        if (s >= p.min_score && p.cls[o] != INT_MIN) {   // (false for NaN; INT_MIN marks taken tracks) - uniform over the lanes
+            const float qx = __fadd_rn(p.centers[o * 2], p.track[o * 2]), qy = __fadd_rn(p.centers[o * 2 + 1], p.track[o * 2 + 1]);
+            const float item = __fmul_rn(p.boxes[o * 4 + 2], p.boxes[o * 4 + 3]);
+            const int c = p.cls[o];
+            float best = __int_as_float(0x7f800000);
+            int bj = INT_MAX;
+            for (int j = lane; j < n_prev; j += 32) {
+                if (pcl[j] != c) continue;
+                const float dx = __fsub_rn(pcx[j], qx), dy = __fsub_rn(pcy[j], qy);
+                const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                if (d > psz[j] || d > item || !(d < best)) continue;   // (strict <: a lane keeps its first minimum)
+                best = d;
+                bj = j;
+            }
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, sft);
+                const int oj = __shfl_xor_sync(0xffffffffu, bj, sft);
+                if (oj != INT_MAX && (bj == INT_MAX || ob < best || (ob == best && oj < bj))) {
+                    best = ob;
+                    bj = oj;
+                }
+            }
+            if (bj != INT_MAX) {
+                found = bj;
+                if (lane == 0) pcl[bj] = INT_MIN;   // taken
+            }
+            __syncwarp();
+        }
+        if (lane == 0) p.match[o] = found;
+    }
+}
+
+}  // namespace
+
+extern "C" int cvm_track_associate(const float* centers, const float* track, const float* boxes, const float* scores, const int32_t* cls,
+                                   int B, int K, float min_score, const float* prev_centers, const float* prev_sizes,
+                                   const int32_t* prev_cls, const int32_t* prev_count, int M, int32_t* match, void* stream) {
+    CVM_CHECK_ARG(B >= 0 && K >= 0 && M >= 0, "bad shape B=%d K=%d M=%d", B, K, M);
+    if (B == 0 || K == 0) return CVM_OK;
+    CVM_CHECK_ARG(centers && track && boxes && scores && cls && match, "NULL pointer argument");
+    CVM_CHECK_ARG(M == 0 || (prev_centers && prev_sizes && prev_cls), "NULL previous-frame argument");
+    const size_t smem = (size_t)M * 16;
+    CVM_CHECK_ARG(smem <= 200 * 1024, "M=%d previous tracks per image do not fit shared memory", M);
+    AssocParams p;
+    p.centers = centers;
+    p.track = track;
+    p.boxes = boxes;
+    p.scores = scores;
+    p.cls = cls;
+    p.prev_centers = prev_centers;
+    p.prev_sizes = prev_sizes;
+    p.prev_cls = prev_cls;
+    p.prev_count = prev_count;
+    p.match = match;
+    p.K = K;
+    p.M = M;
+    p.min_score = min_score;
+    if (smem > 48 * 1024) CVM_CHECK_CUDA(cudaFuncSetAttribute(track_associate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    track_associate_kernel<<<B, 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    CVM_CHECK_LAUNCH("track_associate_kernel");
     return CVM_OK;
 }

@@ -78,6 +78,8 @@ def lib():
     L.cvm_decode_window9.argtypes = [LP, vp, i32, i32, i32, f32, vp, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.cvm_semseg_argmax.restype = i32
     L.cvm_semseg_argmax.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, f64, vp, vp, vp]
+    L.cvm_track_associate.restype = i32
+    L.cvm_track_associate.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, i32, vp, vp]
     _lib = L
     return L
 
@@ -85,7 +87,7 @@ def lib():
 EXPORTS = [
     "cvm_last_error", "cvm_version", "cvm_prepare_objects", "cvm_render_gt", "cvm_render_prev_hm", "cvm_fill_heatmap_inplace", "cvm_loss_workspace_bytes",
     "cvm_loss_fwd", "cvm_loss_finalize", "cvm_loss_bwd", "cvm_decode_topk_workspace_bytes", "cvm_decode_topk",
-    "cvm_decode_window9_workspace_bytes", "cvm_decode_window9", "cvm_semseg_argmax",
+    "cvm_decode_window9_workspace_bytes", "cvm_decode_window9", "cvm_semseg_argmax", "cvm_track_associate",
 ]
 
 

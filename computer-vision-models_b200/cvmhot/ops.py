@@ -242,6 +242,34 @@ def decode_window9(layout: Layout, y_pred, min_conf=0.25, rois_dev=None, max_out
     return out
 
 
+# ---- CenterTrack association -----------------------------------------------------------------------------------------
+def track_associate(det, prev_centers, prev_sizes, prev_cls, prev_count=None, min_score=0.0):
+    """Greedy CenterTrack association (cvm_track_associate).  det: the dict of decode_topk (centers, track, boxes, scores,
+    cls); prev_*: [B,M,2] centres, [B,M,2] (w,h), [B,M] classes of the previous frame's tracks, prev_count [B] valid rows.
+    Returns match [B,K] int32: index of the matched previous track or -1."""
+    if det.get("track") is None:
+        raise _lib.CvmError("track_associate needs the track output of decode_topk (a layout with track_offset)")
+    B, K = (int(v) for v in det["scores"].shape)
+    M = int(prev_centers.shape[1]) if prev_centers.dim() == 3 else 0
+    for name, t, dt in (("centers", det["centers"], torch.float32), ("track", det["track"], torch.float32),
+                        ("boxes", det["boxes"], torch.float32), ("scores", det["scores"], torch.float32),
+                        ("cls", det["cls"], torch.int32), ("prev_centers", prev_centers, torch.float32),
+                        ("prev_sizes", prev_sizes, torch.float32), ("prev_cls", prev_cls, torch.int32)):
+        _need_cuda(t, name, dt)
+        if not t.is_contiguous():
+            raise _lib.CvmError(f"{name} must be contiguous")
+    if prev_count is not None:
+        _need_cuda(prev_count, "prev_count", torch.int32)
+    if tuple(prev_centers.shape) != (B, M, 2) or tuple(prev_sizes.shape) != (B, M, 2) or tuple(prev_cls.shape) != (B, M):
+        raise _lib.CvmError("previous-frame tensors must be [B,M,2], [B,M,2], [B,M]")
+    match = torch.empty((B, K), dtype=torch.int32, device=det["scores"].device)
+    rc = _lib.lib().cvm_track_associate(_ptr(det["centers"]), _ptr(det["track"]), _ptr(det["boxes"]), _ptr(det["scores"]),
+                                        _ptr(det["cls"]), B, K, float(min_score), _ptr(prev_centers), _ptr(prev_sizes),
+                                        _ptr(prev_cls), _ptr(prev_count), M, _ptr(match), _stream())
+    _lib.check(rc, "cvm_track_associate")
+    return match
+
+
 # ---- semseg argmax ---------------------------------------------------------------------------------------------------
 def semseg_argmax(x, off, n_cls, lut_bgr=None, threshold=None, use_weight=False, apply_softmax=True):
     """x [...,C] float32 CUDA. lut_bgr None -> uint8 class ids [...]; else uint8 BGR [...,3] with to_3channel semantics."""

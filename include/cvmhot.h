@@ -18,6 +18,9 @@
  *                        with the fullbox math of models/centernet/post_processing.py:43-52)
  *   cvm_decode_window9   process_2d_output as shipped (post_processing.py:6-66): 9x9 first-argmax + threshold
  *   cvm_semseg_argmax    to_3channel (common/utils/image.py:72-100)
+ *   cvm_track_associate   greedy CenterTrack association of cvm_decode_topk's centre + track_offset with
+ *                        the previous frame's centres; the reference stops at the loss (models/centertracker/__init__.py:5
+ *                        exports params / loss / processor only), so this follows the published algorithm
  *
  * Conventions: all tensors are NHWC, fp32, C-contiguous DEVICE pointers owned by the caller; nothing is allocated,
  * freed or synchronised inside; every call only enqueues work on `stream` (a cudaStream_t / CUstream passed as void*).
@@ -163,6 +166,21 @@ int cvm_decode_window9(const cvm_layout* L, const float* y_pred, int pred_stride
  * mode 1: write BGR u8 [n_pixels,3] with to_3channel semantics (lut_bgr [n_cls,3] device u8; threshold NaN = None). */
 int cvm_semseg_argmax(const float* in, long long n_pixels, int stride, int off, int n_cls, int mode, int apply_softmax,
                       int use_weight, double threshold, const unsigned char* lut_bgr, unsigned char* out, void* stream);
+
+/* ---- CenterTrack association ---------------------------------------------------------------------------------------- */
+/* Greedy matching of the detections of one frame to the tracks of the previous frame, per image, as published with
+ * CenterTrack (Zhou et al., "Tracking Objects as Points", ECCV 2020; src/lib/utils/tracker.py: Tracker.step +
+ * greedy_assignment): detection i (in the given order = score order of cvm_decode_topk) looks for the closest still
+ * unmatched previous centre to  centers[i] + track[i]  (squared distance d in fp32, x term + y term); a pair is invalid
+ * if d > w*h of the previous box, d > w*h of the detection, or the classes differ; ties take the lowest previous index
+ * (numpy argmin).  Detections with score < min_score (or NaN) are skipped.  Consumer of the `track` output of
+ * cvm_decode_topk, whose targets are scattered by CenterTrackerProcess (models/centertracker/processor.py:77-89).
+ *   centers/track [B,K,2], boxes [B,K,4] (tlx,tly,w,h), scores/cls [B,K]: outputs of cvm_decode_topk
+ *   prev_centers [B,M,2], prev_sizes [B,M,2] (w,h), prev_cls [B,M], prev_count [B] (NULL = all M valid)
+ *   match [B,K] int32: index of the matched previous track, -1 = none (a new track, or a skipped detection). */
+int cvm_track_associate(const float* centers, const float* track, const float* boxes, const float* scores, const int32_t* cls,
+                        int B, int K, float min_score, const float* prev_centers, const float* prev_sizes,
+                        const int32_t* prev_cls, const int32_t* prev_count, int M, int32_t* match, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,136 @@
+"""CenterTrack association: oracle hand cases on CPU, cvm_track_associate against the oracle on
+the GPU (bit-exact indices), and the Tracker mirror over a short synthetic sequence.  The reference has no association code,
+so these cases pin the published algorithm (oracle/track_np.py header)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import track_np
+
+
+def _img(cent, sizes, cls, scores=None, track=None):
+    cent = np.asarray(cent, np.float32).reshape(-1, 2)
+    K = cent.shape[0]
+    sizes = np.asarray(sizes, np.float32).reshape(-1, 2)
+    boxes = np.concatenate([cent - sizes / 2, sizes], axis=1).astype(np.float32)
+    scores = np.linspace(0.9, 0.5, K).astype(np.float32) if scores is None else np.asarray(scores, np.float32)
+    track = np.zeros((K, 2), np.float32) if track is None else np.asarray(track, np.float32)
+    return cent, track, boxes, scores, np.asarray(cls, np.int32)
+
+
+def test_oracle_hand_cases():
+    prev_c = np.array([[10, 10], [50, 50], [12, 10]], np.float32)
+    prev_s = np.array([[8, 8], [8, 8], [8, 8]], np.float32)
+    prev_cls = np.array([0, 0, 1], np.int32)
+    # closest-of-class wins; the class-1 detection can only take track 2; far detection stays unmatched
+    c, t, b, s, k = _img([[11, 10], [11, 10], [52, 50], [200, 200]], [[8, 8]] * 4, [0, 1, 0, 0])
+    assert track_np.associate_image(c, t, b, s, k, prev_c, prev_s, prev_cls).tolist() == [0, 2, 1, -1]
+    # greedy order: the first (higher score) detection takes the track although the second is closer
+    c, t, b, s, k = _img([[13, 10], [10, 10]], [[8, 8]] * 2, [0, 0])
+    assert track_np.associate_image(c, t, b, s, k, prev_c[:1], prev_s[:1], prev_cls[:1]).tolist() == [0, -1]
+    # the tracking offset moves the detection back onto the previous centre
+    c, t, b, s, k = _img([[30, 10]], [[8, 8]], [0], track=[[-20, 0]])
+    assert track_np.associate_image(c, t, b, s, k, prev_c, prev_s, prev_cls).tolist() == [0]
+    # radius: squared distance must not exceed either box area (64 here): 8 px away is allowed, 8.1 is not
+    c, t, b, s, k = _img([[18, 10], [58.1, 50]], [[8, 8]] * 2, [0, 0])
+    assert track_np.associate_image(c, t, b, s, k, prev_c, prev_s, prev_cls).tolist() == [0, -1]
+    # a small detection limits the radius too (area 4: only within 2 px)
+    c, t, b, s, k = _img([[13, 10]], [[2, 2]], [0])
+    assert track_np.associate_image(c, t, b, s, k, prev_c, prev_s, prev_cls).tolist() == [-1]
+    # tie in distance: lowest previous index (numpy argmin)
+    pc = np.array([[10, 10], [14, 10]], np.float32)
+    c, t, b, s, k = _img([[12, 10]], [[8, 8]], [0])
+    assert track_np.associate_image(c, t, b, s, k, pc, prev_s[:2], np.zeros(2, np.int32)).tolist() == [0]
+    # score threshold and NaN scores skip the detection; no previous tracks at all
+    c, t, b, s, k = _img([[10, 10], [50, 50]], [[8, 8]] * 2, [0, 0], scores=[0.2, np.nan])
+    assert track_np.associate_image(c, t, b, s, k, prev_c, prev_s, prev_cls, min_score=0.3).tolist() == [-1, -1]
+    assert track_np.associate_image(c, t, b, s, k, prev_c[:0], prev_s[:0], prev_cls[:0]).tolist() == [-1, -1]
+
+
+def _scene(rng, B, K, M, n_cls=4):
+    prev_c = rng.uniform(0, 400, (B, M, 2)).astype(np.float32)
+    prev_s = rng.uniform(2, 60, (B, M, 2)).astype(np.float32)
+    prev_cls = rng.integers(0, n_cls, (B, M)).astype(np.int32)
+    cent = rng.uniform(0, 400, (B, K, 2)).astype(np.float32)
+    sizes = rng.uniform(2, 60, (B, K, 2)).astype(np.float32)
+    cls = rng.integers(0, n_cls, (B, K)).astype(np.int32)
+    track = rng.normal(0, 3, (B, K, 2)).astype(np.float32)
+    for b in range(B):            # most detections are moved previous tracks (so that matches exist), in random order
+        n = min(K, M) * 3 // 4
+        src = rng.permutation(M)[:n]
+        dst = rng.permutation(K)[:n]
+        true_prev = prev_c[b, src]
+        move = rng.normal(0, 6, (n, 2)).astype(np.float32)
+        cent[b, dst] = true_prev + move
+        track[b, dst] = -move + rng.normal(0, 1.0, (n, 2)).astype(np.float32)
+        sizes[b, dst] = prev_s[b, src] * rng.uniform(0.8, 1.2, (n, 2)).astype(np.float32)
+        cls[b, dst] = prev_cls[b, src]
+        if b % 3 == 0 and n > 4:  # exact duplicates: distance ties between previous tracks
+            prev_c[b, src[1]] = prev_c[b, src[0]]
+            prev_cls[b, src[1]] = prev_cls[b, src[0]]
+    scores = np.sort(rng.uniform(0, 1, (B, K)).astype(np.float32), axis=1)[:, ::-1].copy()
+    scores[0, K // 2] = np.nan
+    boxes = np.concatenate([cent - sizes / 2, sizes], axis=2).astype(np.float32)
+    return dict(centers=cent, track=track, boxes=boxes, scores=scores, cls=cls), prev_c, prev_s, prev_cls
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,K,M,seed", [(8, 100, 100, 0), (5, 100, 37, 1), (3, 17, 300, 2), (2, 1, 1, 3), (4, 64, 0, 4)])
+def test_associate_vs_oracle(cuda, B, K, M, seed):
+    from cvmhot import ops
+    rng = np.random.default_rng(seed)
+    det, pc, ps, pk = _scene(rng, B, K, max(M, 1))
+    pc, ps, pk = pc[:, :M], ps[:, :M], pk[:, :M]
+    cnt = rng.integers(0, M + 1, B).astype(np.int32)
+    cnt[0] = M
+    det_d = {k: torch.from_numpy(v).to(cuda) for k, v in det.items()}
+    for count, min_score in ((None, 0.0), (cnt, 0.0), (cnt, 0.4)):
+        got = ops.track_associate(det_d, torch.from_numpy(np.ascontiguousarray(pc)).to(cuda), torch.from_numpy(np.ascontiguousarray(ps)).to(cuda),
+                                  torch.from_numpy(np.ascontiguousarray(pk)).to(cuda), None if count is None else torch.from_numpy(count).to(cuda),
+                                  min_score).cpu().numpy()
+        ref = track_np.associate(det, pc, ps, pk, count, min_score)
+        assert np.array_equal(got, ref)
+        if M > 0 and count is None and min_score == 0.0 and K > 10:
+            assert (got >= 0).sum() > 0                                   # the scenes do contain matches
+        for b in range(B):                                                # a previous track is matched at most once
+            m = got[b][got[b] >= 0]
+            assert len(set(m.tolist())) == len(m)
+
+
+@pytest.mark.gpu
+def test_tracker_keeps_ids_over_frames(cuda):
+    """Three frames of objects drifting by a known motion: decode-like dicts with exact tracking offsets -> the ids of
+    frame 0 survive, an object that appears later gets a fresh id, low-score clutter stays untracked."""
+    from cvmhot.models.centertracker import Tracker
+    rng = np.random.default_rng(5)
+    B, K, n = 2, 16, 6
+    pos = rng.uniform(60, 300, (B, n, 2)).astype(np.float32)
+    pos[:, :, 0] += np.arange(n, dtype=np.float32)[None, :] * 40          # well separated
+    vel = rng.uniform(-4, 4, (B, n, 2)).astype(np.float32)
+    tracker = Tracker(min_score=0.1, new_thresh=0.3)
+    seen = []
+    for f in range(3):
+        n_f = n if f < 2 else n + 1                                       # a newcomer in the last frame
+        cent = np.full((B, K, 2), -1000, np.float32)
+        cur = pos + vel * f
+        cent[:, :n] = cur
+        if f == 2:
+            cent[:, n] = [350, 20]
+        perm = np.stack([rng.permutation(n_f) for _ in range(B)])
+        cent[:, :n_f] = np.take_along_axis(cent[:, :n_f], perm[..., None], axis=1)
+        track = np.zeros((B, K, 2), np.float32)
+        track[:, :n_f] = np.take_along_axis(np.concatenate([-vel, np.zeros((B, 1, 2), np.float32)], axis=1)[:, :n_f], perm[..., None], axis=1)
+        sizes = np.full((B, K, 2), 20, np.float32)
+        scores = np.zeros((B, K), np.float32)
+        scores[:, :n_f] = 0.8
+        scores[:, n_f:n_f + 2] = 0.2                                       # clutter below new_thresh
+        det = dict(centers=cent, track=track, boxes=np.concatenate([cent - sizes / 2, sizes], 2).astype(np.float32), scores=scores,
+                   cls=np.zeros((B, K), np.int32))
+        ids = tracker.step({k: torch.from_numpy(v).to(cuda) for k, v in det.items()}).cpu().numpy()
+        inv = np.argsort(perm, axis=1)                                    # ids in object order
+        seen.append(np.take_along_axis(ids[:, :n_f], inv, axis=1))
+        assert (ids[:, n_f:] == 0).all()
+    assert (seen[0] > 0).all() and all(len(set(r.tolist())) == n for r in seen[0])
+    assert np.array_equal(seen[1], seen[0])
+    assert np.array_equal(seen[2][:, :n], seen[0])
+    assert (seen[2][:, n] == n + 1).all()
