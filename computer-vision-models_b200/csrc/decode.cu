@@ -68,6 +68,7 @@ struct DecodeParams {
     unsigned int thr0_bits;       // initial threshold score bits (1 = smallest positive float; experiments only raise it)
     float inv_W;                  // 1 / W
     int rescan_step;              // appends after which the score histogram is scanned again (test_hits)
+    int dbg;                      // experiment knob CVM_DECODE_DBG: 1 = no pixel scan, 2 = no hit test, 4 = no threshold upkeep
 };
 
 // Fixed-size head of the dynamic shared memory block; the ring, the candidate buffer, the select scratch and the score
@@ -142,7 +143,7 @@ __device__ unsigned long long g_decode_stats[16];
 #define STAT_FLUSH() ((void)0)
 #endif
 #ifdef CVM_DECODE_STATS
-#define TH_MARK(i) do { const long long t_ = clock64(); if ((threadIdx.x & 31) == 0) atomicAdd(&g_decode_stats[i], (unsigned long long)(t_ - th_t)); th_t = clock64(); } while (0)
+#define TH_MARK(i) do { const long long t_ = clock64(); if ((threadIdx.x & 31) == 0) { atomicAdd(&g_decode_stats[i], (unsigned long long)(t_ - th_t)); if ((i) == 12) atomicAdd(&g_decode_stats[8], 1ull); } th_t = clock64(); } while (0)
 #define TH_START() long long th_t = clock64()
 #else
 #define TH_MARK(i) ((void)0)
@@ -440,6 +441,52 @@ __device__ __forceinline__ mask_t<HM> channel_mask(const float* px, int hm, floa
     return m;
 }
 
+// Append the peaks found in one round (peak[k] of this lane's k-th pixel, channel ch[k], score v[k]) to the candidate buffer:
+// one shared atomic per warp, keys placed by ballot rank.  Warp-uniform call (pm[k] = ballot of peak[k], total = their sum > 0).
+// Ends at a safe point: joins a pending compaction, or rescans the score histogram when enough keys have come in.
+template <int HM, int NH>
+__device__ __forceinline__ void append_peaks(const DecodeParams& p, const Hit<HM> (&hit)[NH], const bool (&peak)[NH], const float (&v)[NH],
+                                             const int (&ch)[NH], const unsigned (&pm)[NH], unsigned total) {
+    SharedHead* h = sm_head();
+    unsigned long long* cand = sm_cand(p);
+    unsigned int* shist = sm_shist(p);
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    int rescan = 0;
+    TH_START();
+    if (lane == 0) {
+        base = (unsigned)atomicAdd(&h->count, (int)total);
+        const int cnt = (int)(base + total);
+        rescan = cnt >= p.K && cnt - *(volatile int*)&h->scanned >= p.rescan_step;
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    rescan = __shfl_sync(0xffffffffu, rescan, 0);
+    TH_MARK(12);
+#pragma unroll
+    for (int k = 0; k < NH; ++k) {
+        if (peak[k]) {
+            const unsigned pos = base + __popc(pm[k] & ((1u << lane) - 1u));
+            const unsigned bits = __float_as_uint(v[k]);
+            const unsigned flat = (unsigned)hit[k].q * (unsigned)p.hm + (unsigned)ch[k];
+            cand[pos] = ((unsigned long long)bits << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
+            if (pos >= (unsigned)p.compact_at) *(volatile int*)&h->compact_flag = 1;
+            const unsigned bin = bits >> kScoreShift;
+            atomicAdd(&shist[bin], 1u);
+            atomicMax(&h->maxbin, (int)bin);   // (no result used: nothing waits for it)
+        }
+        base += __popc(pm[k]);
+    }
+    // Safe point after every batch of appends: once the buffer has passed its mark, a warp adds at most these <= 32 * NH
+    // keys before it joins the compaction, which bounds the buffer (see plan_decode).
+    TH_MARK(13);
+    __syncwarp();
+    const bool must_gather = __any_sync(0xffffffffu, load_ctrl(h).y != 0);
+    TH_MARK(14);
+    if (must_gather) gather(p, false, 0);
+    else if (rescan) scan_threshold(h, shist, p.K, lane);
+    TH_MARK(15);
+}
+
 // Exact 3x3 test of the pending hits of a warp (NH pixels per lane) and append of the peaks.  Called by ALL lanes of the
 // warp (lanes without a hit pass mask 0).  Every round each pixel tests ONE of its pending channels (the channels differ
 // between lanes, the control flow does not: the loop condition is a vote, the ballots and the aggregated append - one
@@ -461,9 +508,69 @@ __device__ __forceinline__ int test_hits(const DecodeParams& p, long long img, c
     TH_START();
     SharedHead* h = sm_head();
     const float* ring = sm_ring();
-    unsigned long long* cand = sm_cand(p);
-    unsigned int* shist = sm_shist(p);
+    // ---- fast path (nearly every call once the segment has a threshold): each hit pixel of the warp has ONE pending
+    //      channel and its 3x3 neighbourhood is inside the map.  Straight-line code: the nine
+    //      loads are issued while the row / column of the pixel is still being worked out, a vote confirms that nobody was
+    //      at the border, and three quarters of the calls end at the ballot because no hit was a peak. ----
+    if (p.ring_nb && __float_as_uint(thr_f) != p.thr0_bits) {
+        const int W = p.W, stride = p.stride, ring_px = p.S * p.T;
+        bool cheap = true;
+#pragma unroll
+        for (int k = 0; k < NH; ++k)
+            if (rem[k]) cheap = cheap && (rem[k] & (rem[k] - 1)) == 0;
+        if (__all_sync(0xffffffffu, cheap)) {
+            bool peak[NH], border = false;
+            float v[NH];
+            int ch[NH];
+            unsigned pm[NH], total = 0;
+#pragma unroll
+            for (int k = 0; k < NH; ++k) {
+                peak[k] = false;
+                v[k] = 0.f;
+                ch[k] = 0;
+                if (rem[k]) {
+                    ch[k] = lowest_bit(rem[k]);
+                    // ring positions of the three rows' centre pixels and of their left / right neighbours (the ring is a
+                    // circular buffer of pixels: every step may wrap)
+                    const int mid = hit[k].rp;
+                    int up = mid - W, dn = mid + W;
+                    up += up < 0 ? ring_px : 0;
+                    dn -= dn >= ring_px ? ring_px : 0;
+                    const int ul = up == 0 ? ring_px - 1 : up - 1, ur = up == ring_px - 1 ? 0 : up + 1;
+                    const int ml = mid == 0 ? ring_px - 1 : mid - 1, mr = mid == ring_px - 1 ? 0 : mid + 1;
+                    const int dl = dn == 0 ? ring_px - 1 : dn - 1, dr = dn == ring_px - 1 ? 0 : dn + 1;
+                    const float* c = ring + ch[k];
+                    const float a0 = c[ul * stride], a1 = c[up * stride], a2 = c[ur * stride], a3 = c[ml * stride], a4 = c[mr * stride],
+                                a5 = c[dl * stride], a6 = c[dn * stride], a7 = c[dr * stride];
+                    v[k] = c[mid * stride];
+                    const int q = hit[k].q;
+                    int y = __float2int_rz(__fmul_rn((float)q, p.inv_W)), x = q - y * W;   // exact after one correction step
+                    if (x < 0) {
+                        --y;
+                        x += W;
+                    } else if (x >= W) {
+                        ++y;
+                        x -= W;
+                    }
+                    border = border || !(y > 0 && y < p.H - 1 && x > 0 && x < W - 1);
+                    const float m = fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), fmaxf(fmaxf(a4, a5), fmaxf(a6, a7)));
+                    peak[k] = v[k] >= thr_f && m <= v[k];
+                }
+            }
+            if (!__any_sync(0xffffffffu, border)) {
+#pragma unroll
+                for (int k = 0; k < NH; ++k) {
+                    pm[k] = __ballot_sync(0xffffffffu, peak[k]);
+                    total += __popc(pm[k]);
+                }
+                if (total) append_peaks<HM, NH>(p, hit, peak, v, ch, pm, total);
+                return 1;
+            }
+        }
+    }
     const int lane = threadIdx.x & 31;
+    (void)lane;
+    (void)h;
     int nb[NH][8];
     const float* g_px[NH];
     M pref[NH];
@@ -481,8 +588,6 @@ __device__ __forceinline__ int test_hits(const DecodeParams& p, long long img, c
             }
         }
     }
-    TH_MARK(12);
-    TH_MARK(9);
     do {
         bool peak[NH];
         float v[NH];
@@ -502,38 +607,7 @@ __device__ __forceinline__ int test_hits(const DecodeParams& p, long long img, c
             pm[k] = __ballot_sync(0xffffffffu, peak[k]);
             total += __popc(pm[k]);
         }
-        TH_MARK(13);
-        if (total) {
-            unsigned base = 0;
-            int rescan = 0;
-            if (lane == 0) {
-                base = (unsigned)atomicAdd(&h->count, (int)total);
-                const int cnt = (int)(base + total);
-                rescan = cnt >= p.K && cnt - *(volatile int*)&h->scanned >= p.rescan_step;
-            }
-            base = __shfl_sync(0xffffffffu, base, 0);
-            rescan = __shfl_sync(0xffffffffu, rescan, 0);
-#pragma unroll
-            for (int k = 0; k < NH; ++k) {
-                if (peak[k]) {
-                    const unsigned pos = base + __popc(pm[k] & ((1u << lane) - 1u));
-                    const unsigned bits = __float_as_uint(v[k]);
-                    const unsigned flat = (unsigned)hit[k].q * (unsigned)p.hm + (unsigned)ch[k];
-                    cand[pos] = ((unsigned long long)bits << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
-                    if (pos >= (unsigned)p.compact_at) *(volatile int*)&h->compact_flag = 1;
-                    const unsigned bin = bits >> kScoreShift;
-                    atomicAdd(&shist[bin], 1u);
-                    if ((int)bin > *(volatile int*)&h->maxbin) atomicMax(&h->maxbin, (int)bin);
-                }
-                base += __popc(pm[k]);
-            }
-            // Safe point after every batch of appends: once the buffer has passed its mark, a warp adds at most these
-            // <= 32 * NH keys before it joins the compaction, which bounds the buffer (see plan_decode).
-            __syncwarp();
-            if (__any_sync(0xffffffffu, load_ctrl(h).y != 0)) gather(p, false, 0);
-            else if (rescan) scan_threshold(h, shist, p.K, lane);
-        }
-        TH_MARK(14);
+        if (total) append_peaks<HM, NH>(p, hit, peak, v, ch, pm, total);
         // the threshold may have moved (our rescan, another warp's, a compaction): drop the pending channels below it
         const unsigned now_bits = __shfl_sync(0xffffffffu, load_ctrl(h).x, 0);
         if (now_bits > __float_as_uint(thr_f)) {
@@ -546,7 +620,6 @@ __device__ __forceinline__ int test_hits(const DecodeParams& p, long long img, c
 #pragma unroll
         for (int k = 0; k < NH; ++k) any |= rem[k];
         ++rounds;
-        TH_MARK(15);
     } while (__any_sync(0xffffffffu, any != 0));
     return rounds;   // statistics only
 }
@@ -592,8 +665,8 @@ __device__ __noinline__ void gather(const DecodeParams& p, bool at_segment_end, 
         bool seg;
         __device__ ~GatherTimer() {
             if ((threadIdx.x & 31) == 0) {
-                atomicAdd(&g_decode_stats[seg ? 10 : 8], (unsigned long long)(clock64() - t0));
-                atomicAdd(&g_decode_stats[seg ? 11 : 9], 1ull);
+                if (seg) atomicAdd(&g_decode_stats[10], (unsigned long long)(clock64() - t0));
+                if (seg) atomicAdd(&g_decode_stats[11], 1ull);
             }
         }
     } g_timer{g_t0, at_segment_end};
@@ -785,7 +858,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
             cur[k].mask = 0;
             cur[k].q = q0 + tid;
             cur[k].rp = sl * T + tid;   // ring position of this lane's pixel
-            if (k < gc && tid < min(T, HW - q0)) {
+            if (k < gc && tid < min(T, HW - q0) && !(p.dbg & 1)) {
                 const float* px = ring + (size_t)cur[k].rp * stride;
                 cur[k].vmax = pixel_max<STRIDE, HM>(px, p.hm);
                 if (cur[k].vmax >= z.thr_f) cur[k].mask = channel_mask<HM>(px, p.hm, z.thr_f);
@@ -806,7 +879,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
         STAT_ADD(5, n_rounds);
         if (was_young) { STAT_END(7); } else { STAT_END(2); }
 #else
-        test_hits<HM, GPS>(p, img, cur, z.thr_f);
+        if (!(p.dbg & 2)) test_hits<HM, GPS>(p, img, cur, z.thr_f);
 #endif
         STAT_BEGIN();
         const bool segment_end = (st + 1 == spi) || (i + 1 == n_local);
@@ -818,7 +891,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
         z.thr_f = __uint_as_float(ctrl.x);   // stale values are still valid bounds
         DBG_STATE(103 + i * 1000);
         if (!segment_end) {
-            if (warp == 1) scan_threshold(h, sm_shist(p), p.K, lane);
+            if (warp == 1 && !(p.dbg & 4)) scan_threshold(h, sm_shist(p), p.K, lane);
             if (__any_sync(0xffffffffu, ctrl.y != 0)) {   // a vote: the decision to gather must be warp-uniform
                 gather(p, false, 0);
                 z.thr_f = __uint_as_float(load_ctrl(h).x);
@@ -1122,6 +1195,7 @@ extern "C" int cvm_decode_topk(const cvm_layout* L, const float* y_pred, int pre
     p.counts = reinterpret_cast<int*>(static_cast<unsigned char*>(ws) + t.ws_keys);
     p.thr0_bits = 1u;
     p.inv_W = 1.0f / (float)L->W;
+    p.dbg = env_int("CVM_DECODE_DBG", 0);
     p.rescan_step = env_int("CVM_DECODE_RESCAN", K / 4 > 8 ? K / 4 : 8);
     if (const char* e = getenv("CVM_DECODE_THR0")) {   // experiment knob (results are wrong when set): start threshold
         const float f = (float)atof(e);

@@ -21,7 +21,7 @@ ops.decode_topk(L, yp, K=100)
 lib.cvm_decode_stats(out, 1)
 v = list(out)
 ws = v[6]
-names = ["wait cycles", "scan cycles", "test_hits cycles (threshold set)", "tail (release/threshold/gather) cycles", "pixel hits", "test rounds", "warp-steps", "test_hits cycles (no threshold yet)", "gather cycles (compaction)", "gather calls (compaction, per warp)", "gather cycles (segment end)", "gather calls (segment end, per warp)", "test_hits: prologue", "test_hits: peak tests", "test_hits: append", "test_hits: threshold refresh"]
+names = ["wait cycles", "scan cycles", "test_hits cycles (threshold set)", "tail (release/threshold/gather) cycles", "pixel hits", "test rounds", "warp-steps", "test_hits cycles (no threshold yet)", "append calls", "-", "gather cycles (segment end)", "gather calls (segment end, per warp)", "append: count atomic + shuffles", "append: key / histogram stores", "append: syncwarp + flag vote", "append: rescan"]
 for n, x in zip(names, v):
     print(f"{n:45s} {x:14d}  per warp-step {x / max(ws, 1):10.1f}")
 print("pixel hits per image", v[4] / B)
