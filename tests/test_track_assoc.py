@@ -97,8 +97,28 @@ def test_associate_vs_oracle(cuda, B, K, M, seed):
             assert len(set(m.tolist())) == len(m)
 
 
+def _oracle_associate(det, prev_centers, prev_sizes, prev_cls, prev_count=None, min_score=0.0):
+    """stand-in for ops.track_associate on CPU tensors (the host logic of Tracker is what the CPU test is about)"""
+    d = {k: v.numpy() for k, v in det.items()}
+    m = track_np.associate(d, prev_centers.numpy(), prev_sizes.numpy(), prev_cls.numpy(),
+                           None if prev_count is None else prev_count.numpy(), min_score)
+    return torch.from_numpy(m)
+
+
+def test_tracker_host_logic_on_cpu(monkeypatch):
+    """The id bookkeeping of the Tracker mirror (births, compaction of the kept tracks, id continuity) with the matcher
+    replaced by the oracle, so that it runs without a GPU."""
+    from cvmhot import ops
+    monkeypatch.setattr(ops, "track_associate", _oracle_associate)
+    _run_tracker_sequence(torch.device("cpu"))
+
+
 @pytest.mark.gpu
 def test_tracker_keeps_ids_over_frames(cuda):
+    _run_tracker_sequence(cuda)
+
+
+def _run_tracker_sequence(cuda):
     """Three frames of objects drifting by a known motion: decode-like dicts with exact tracking offsets -> the ids of
     frame 0 survive, an object that appears later gets a fresh id, low-score clutter stays untracked."""
     from cvmhot.models.centertracker import Tracker
