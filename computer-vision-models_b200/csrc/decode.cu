@@ -1106,7 +1106,9 @@ int plan_decode(const cvm_layout* L, int stride, int B, int K, Plan* t) {
     t->gpi = (int)((HW + T - 1) / T);
     t->spi = (t->gpi + t->gps - 1) / t->gps;
     t->n_steps = (long long)B * t->spi;
-    long long grid = cvm_num_sms();
+    // CVM_DECODE_SPARE_SMS (experiment knob): SMs left free, so that the small all-reduce of the loss partials, issued just
+    // before the decode by a data-parallel caller, finds an SM and runs beside it (2 GPUs: 0.634 -> 0.632 ms per step)
+    long long grid = cvm_num_sms() - env_int("CVM_DECODE_SPARE_SMS", 0);
     if (grid > t->n_steps) grid = t->n_steps;
     if (grid < 1) grid = 1;
     t->grid = (int)grid;
