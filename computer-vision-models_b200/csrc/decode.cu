@@ -68,7 +68,7 @@ struct DecodeParams {
     unsigned int thr0_bits;       // initial threshold score bits (1 = smallest positive float; experiments only raise it)
     float inv_W;                  // 1 / W
     int rescan_step;              // appends after which the score histogram is scanned again (test_hits)
-    int dbg;                      // experiment knob CVM_DECODE_DBG: 1 = no pixel scan, 2 = no hit test, 4 = no threshold upkeep
+    int dbg;                      // experiment knob CVM_DECODE_DBG: 1 = no pixel scan, 2 = no hit test, 4 = also rescan the histogram at every step
 };
 
 // Fixed-size head of the dynamic shared memory block; the ring, the candidate buffer, the select scratch and the score
@@ -493,7 +493,7 @@ __device__ __forceinline__ void append_peaks(const DecodeParams& p, const Hit<HM
 // shared atomic per warp and round - are warp-uniform); the NH pixels of a lane are tested side by side (independent load
 // chains).  While the segment has no threshold yet (`thr_f` is the initial one) the first round takes each pixel's
 // LARGEST channel: the first K peaks found that way are high ones, and the threshold they give prunes most of the rest.
-// The warp that pushes the count K / 4 past the last histogram scan rescans, and the pending channels are re-filtered
+// The warp that pushes the count K / 2 past the last histogram scan rescans, and the pending channels are re-filtered
 // whenever the threshold has moved.  img: image of the pixels; thr_f: in/out, the warp's current threshold.
 template <int HM, int NH>
 __device__ __forceinline__ int test_hits(const DecodeParams& p, long long img, const Hit<HM> (&hit)[NH], float& thr_f) {
@@ -891,7 +891,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
         z.thr_f = __uint_as_float(ctrl.x);   // stale values are still valid bounds
         DBG_STATE(103 + i * 1000);
         if (!segment_end) {
-            if (warp == 1 && !(p.dbg & 4)) scan_threshold(h, sm_shist(p), p.K, lane);
+            // (the histogram is rescanned by the appending warps, test_hits; a rescan by one warp at every step on top of that
+            // cost 4 % - an out-of-line call spills live registers, and local memory is an L2 round trip here)
+            if (warp == 1 && (p.dbg & 4)) scan_threshold(h, sm_shist(p), p.K, lane);
             if (__any_sync(0xffffffffu, ctrl.y != 0)) {   // a vote: the decision to gather must be warp-uniform
                 gather(p, false, 0);
                 z.thr_f = __uint_as_float(load_ctrl(h).x);
@@ -1198,7 +1200,7 @@ extern "C" int cvm_decode_topk(const cvm_layout* L, const float* y_pred, int pre
     p.thr0_bits = 1u;
     p.inv_W = 1.0f / (float)L->W;
     p.dbg = env_int("CVM_DECODE_DBG", 0);
-    p.rescan_step = env_int("CVM_DECODE_RESCAN", K / 4 > 8 ? K / 4 : 8);
+    p.rescan_step = env_int("CVM_DECODE_RESCAN", K / 2 > 8 ? K / 2 : 8);
     if (const char* e = getenv("CVM_DECODE_THR0")) {   // experiment knob (results are wrong when set): start threshold
         const float f = (float)atof(e);
         memcpy(&p.thr0_bits, &f, 4);
