@@ -227,7 +227,7 @@ __device__ __noinline__ void select_topk(unsigned long long* keys, int n, int K,
 // entry is a real peak of this image, so a later candidate below the lower edge of tb cannot make the top K: the edge
 // becomes the new threshold.  Counts read while other warps append are at worst too low, which only makes the bound
 // conservative.  No buffer traffic, no CTA-wide sync.
-__device__ __noinline__ void scan_threshold(SharedHead* h, const unsigned int* shist, int K, int lane) {
+__device__ __forceinline__ void scan_threshold(SharedHead* h, const unsigned int* shist, int K, int lane) {
     int n = 0, top = 0;
     if (lane == 0) {   // one lane decides (the words change under our feet), the warp follows
         n = *(volatile const int*)&h->count;
