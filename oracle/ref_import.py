@@ -11,6 +11,9 @@ MagicMock stubs, so that the NumPy/numba parts of the hot path run exactly as sh
   Roi, convert_back_to_roi common/utils/image.py:9-28
   CenternetParams         models/centernet/params.py:10
   CentertrackerParams     models/centertracker/params.py:3
+  CenternetLoss           models/centernet/loss.py:6-155      (executed over oracle/tf_shim.py: TF ops on torch-CPU fp32)
+  CentertrackerLoss       models/centertracker/loss.py:7-28   (same)
+  MultitaskLoss           models/multitask/loss.py:13-47      (same; only calc_centernet is used)
 
 This only works in the build container (/root/reference does not exist on the GPU box); it is
 used by tests/golden/make_golden.py to generate the committed fixtures and by CPU tests that
@@ -30,7 +33,8 @@ _STUBS = [
     "tensorflow.python.keras.engine", "tensorflow.python.eager",
     "matplotlib", "matplotlib.pyplot", "albumentations", "pymongo", "pymongo.database",
     "pymongo.collection", "pygame", "redis", "tensorflow_model_optimization",
-    "tflite_runtime", "tflite_runtime.interpreter", "pycoral", "pycoral.utils",
+    "tflite_runtime", "tflite_runtime.interpreter", "pycoral", "pycoral.utils", "segmentation_models",
+    "tensorflow.keras.applications", "tensorflow.keras.backend", "tensorflow.keras.metrics",
 ]
 
 
@@ -47,6 +51,8 @@ def load():
         return _cache
     if not available():
         raise RuntimeError(f"reference not mounted at {REFERENCE_ROOT}")
+    from . import tf_shim
+    tf_shim.install()            # tensorflow, tensorflow.math/nn/keras/keras.losses: real semantics over torch fp32
     for name in _STUBS:
         if name not in sys.modules:
             sys.modules[name] = MagicMock()
@@ -59,10 +65,19 @@ def load():
     from models.centernet.post_processing import process_2d_output
     from models.centertracker.params import CentertrackerParams
     from common.utils.image import to_3channel, Roi, convert_back_to_roi
+    from models.centernet.loss import CenternetLoss
+    from models.centertracker.loss import CentertrackerLoss
     _cache.update(dict(
         CenternetParams=CenternetParams, CentertrackerParams=CentertrackerParams,
         fill_heatmap=fill_heatmap, ProcessImages=ProcessImages,
         process_2d_output=process_2d_output, to_3channel=to_3channel,
         Roi=Roi, convert_back_to_roi=convert_back_to_roi,
+        CenternetLoss=CenternetLoss, CentertrackerLoss=CentertrackerLoss,
     ))
+    try:        # the multitask package pulls in more of the reference (semseg/depth params, label spec); optional
+        from models.multitask.loss import MultitaskLoss
+        from models.multitask.params import MultitaskParams
+        _cache.update(MultitaskLoss=MultitaskLoss, MultitaskParams=MultitaskParams)
+    except Exception as e:      # pragma: no cover
+        _cache["MultitaskLoss_error"] = repr(e)
     return _cache

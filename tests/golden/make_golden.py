@@ -117,8 +117,160 @@ def gen_to3(r, seed):
     return out
 
 
+# ---- loss: the UNMODIFIED reference loss files executed over oracle/tf_shim.py (TF ops on torch-CPU fp32) ----------------
+_POS_ATTRS = ("class_pos", "r_offset_pos", "fullbox_pos", "l_shape_pos", "radial_dist_pos", "orientation_pos",
+              "obj_dims_pos", "track_offset_pos")
+
+
+def ref_loss_object(r, nb, hm=1, track=False, l_shape=False, info3d=False):
+    """CenternetLoss / CentertrackerLoss of the reference (models/centernet/loss.py:6-29, centertracker/loss.py:7-14).
+    hm > 1 (Profile N): the reference hard-codes ONE heatmap channel (params.py:56, loss.py:12); the per-class-heatmap
+    layout is run through the very same reference lines by switching the class field off and moving the channel
+    positions the constructor pre-computed (instance attributes only, the class and its methods stay untouched)."""
+    P = (r["CentertrackerParams"] if track else r["CenternetParams"])(nb)
+    P.REGRESSION_FIELDS["l_shape"].active = l_shape
+    P.REGRESSION_FIELDS["3d_info"].active = info3d
+    if hm > 1:
+        P.REGRESSION_FIELDS["class"].active = False
+    loss = (r["CentertrackerLoss"] if track else r["CenternetLoss"])(P)
+    if hm > 1:
+        loss.obj_pos = [0, hm]
+        for a in _POS_ATTRS:
+            if hasattr(loss, a):
+                v = getattr(loss, a)
+                setattr(loss, a, [x + hm - 1 for x in v] if isinstance(v, list) else v + hm - 1)
+    return loss, P
+
+
+def ref_loss_values(loss, y_true, y_pred):
+    """Every public term of the reference loss on one (y_true with weights plane, y_pred) pair -> dict of python floats."""
+    import torch
+    yt = torch.from_numpy(np.ascontiguousarray(y_true, np.float32))
+    yp = torch.from_numpy(np.ascontiguousarray(y_pred, np.float32))
+    out = {"total": float(loss(y_true, y_pred)),                                            # Loss.__call__ -> call, loss.py:133-155
+           "focal_weighted": float(loss.obj_focal_loss(yt[..., :-1], yp, yt[..., -1])),     # as call uses it, :137-140
+           "focal_metric": float(loss.obj_focal_loss(yt, yp))}                              # as a Keras metric, train.py:62
+    for name in ("class", "r_offset", "fullbox", "l_shape", "radial_dist", "orientation", "obj_dims", "track_offset"):
+        pos = {"radial_dist": "radial_dist_pos", "orientation": "orientation_pos", "obj_dims": "obj_dims_pos"}.get(name, name + "_pos")
+        if hasattr(loss, pos):
+            out[name] = float(getattr(loss, name + "_loss")(yt[..., :-1], yp))
+    return out
+
+
+def _pack_cases(cases):
+    """cases: {name: (y_true, y_pred, values dict)} -> flat dict for np.savez (pred stored as given dtype)."""
+    out = {"cases": np.array(sorted(cases))}
+    for name, (yt, yp, vals) in cases.items():
+        out[name + "/y_true"] = yt
+        out[name + "/y_pred"] = yp
+        out[name + "/terms"] = np.array(sorted(vals))
+        out[name + "/values"] = np.array([vals[k] for k in sorted(vals)], np.float64)
+    return out
+
+
+def gen_loss_fixture(r):
+    """The reference's own test inputs (loss_test.py:9-49, centertracker/loss_test.py:10-21 with the track channels in
+    the intended place, before the weights plane) and the perturbations its tests apply."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from fixtures import reference_loss_fixture
+    cases = {}
+    for track in (False, True):
+        nb, gt, perfect = reference_loss_fixture(track=track)
+        loss, P = ref_loss_object(r, nb, track=track, l_shape=True, info3d=True)
+        assert P.mask_channels() + 1 == gt.shape[-1]
+        tag = "trk_" if track else ""
+        preds = {"perfect": perfect}
+        p = perfect.copy(); p[0, 1, 1, 0] = 0.8; preds["peak08"] = p               # loss_test.py:57
+        p = perfect.copy(); p[0, 2, 1, 0] = 1.0; preds["one_off"] = p              # :62
+        p = perfect.copy(); p[0, 6, 1, 0] = 1.0; preds["wrong_peak"] = p           # :65-66
+        p = perfect.copy(); p[0, 1, 1, 2] = 0.8; preds["class08"] = p              # :74
+        p = perfect.copy(); p[0, 1, 1, 3] = 1.0; preds["class_wrong"] = p          # :79
+        p = perfect.copy(); p[0, 1, 1, 6] = 2.2 - 30; preds["box_far"] = p         # :89
+        p = perfect.copy(); p[0, 1, 1, 5:20] += np.linspace(-1.5, 2.5, 15).astype(np.float32); preds["all_fields_off"] = p
+        if track:
+            p = perfect.copy(); p[0, 1, 1, 20:22] = [0.0, 3.0]; preds["track_off"] = p   # centertracker/loss_test.py:28-30
+        for k, pr in preds.items():
+            cases[tag + k] = (gt, pr, ref_loss_values(loss, gt, pr))
+    return _pack_cases(cases)
+
+
+def _synth_batch(nb, profile, H, W, B, config, track=False, l_shape=False, info3d=False, n_obj=None):
+    from oracle import render_np
+    from oracle.layout import make_layout
+    import synth
+    Lo = make_layout(H, W, nb, profile, track=track, l_shape=l_shape, info3d=info3d)
+    data = synth.make_batch(Lo, config, B, n_obj=n_obj, track=track)
+    yt = np.stack([render_np.render_image(Lo, data["boxes"][i], data["cls"][i], data["ignore"][i],
+                                          data["track"][i] if track else None) for i in range(B)])
+    return Lo, yt, data["y_pred"]
+
+
+def gen_loss_maps(r):
+    """Full-size and odd-size maps: y_true from the render oracle (itself pinned bit-exact to the real render), y_pred
+    synthetic (SURVEY 8d distributions) rounded to fp16-representable values so the fixture stays small."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    cases = {}
+    rng = np.random.default_rng(77)
+    for name, nb, profile, H, W, B, kw in (
+            ("profile_r_128x384", 10, "R", 128, 384, 1, {}),
+            ("profile_n_128x384", 10, "N", 128, 384, 1, {}),
+            ("tracker_n_64x96", 10, "N", 64, 96, 2, dict(track=True)),
+            ("tracker_r_37x53", 6, "R", 37, 53, 3, dict(track=True)),
+            ("all_fields_r_32x48", 4, "R", 32, 48, 3, dict(track=True, l_shape=True, info3d=True))):
+        Lo, yt, yp = _synth_batch(nb, profile, H, W, B, 7, **kw)
+        # targets for the fields the render does not fill (l_shape / 3d_info): random values at the peak pixels
+        pm = (yt[..., :Lo.hm] == 1.0).any(-1)
+        for f in Lo.fields:
+            if f.name in ("l_shape", "radial_dist", "orientation", "obj_dims"):
+                yt[..., f.off:f.off + f.size][pm] = rng.normal(0, 3, (int(pm.sum()), f.size)).astype(np.float32)
+        yp = yp.astype(np.float16)
+        loss, P = ref_loss_object(r, nb, hm=Lo.hm, **kw)
+        assert P.mask_channels() + (Lo.hm - 1) == Lo.Cp, (P.mask_channels(), Lo.Cp)
+        cases[name] = (yt, yp, ref_loss_values(loss, yt, yp.astype(np.float32)))
+    # no object anywhere: the n == 0 branches of tf.cond (loss.py:59,130)
+    Lo, yt, yp = _synth_batch(5, "R", 16, 24, 2, 8, n_obj=0)
+    yt[..., 0] = rng.uniform(0, 0.9, yt.shape[:-1]).astype(np.float32)
+    loss, _ = ref_loss_object(r, 5)
+    yp = yp.astype(np.float16)
+    cases["no_objects_r_16x24"] = (yt, yp, ref_loss_values(loss, yt, yp.astype(np.float32)))
+    # clip edges of the log arguments and exact 0 / 1 predictions (loss.py:41,47)
+    Lo, yt, yp = _synth_batch(3, "N", 9, 11, 2, 9)
+    yp[0, 0, 0, 0], yp[0, 0, 1, 0], yp[0, 0, 2, 0], yp[0, 0, 3, 0] = 0.0, 1.0, 0.01, 0.99
+    yp[1, 4, 4, :3] = [0.005, 0.995, 0.5]
+    yp = yp.astype(np.float16)
+    loss, _ = ref_loss_object(r, 3, hm=3)
+    cases["clip_edges_n_9x11"] = (yt, yp, ref_loss_values(loss, yt, yp.astype(np.float32)))
+    return _pack_cases(cases)
+
+
+def gen_loss_multitask(r):
+    """MultitaskLoss.calc_centernet (models/multitask/loss.py:44-47): the CenterNet slice of the wide multitask tensors."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import torch
+    nb = 7
+    mp = r["MultitaskParams"](nb)
+    ml = r["MultitaskLoss"](mp)
+    Ccn = mp.cn_params.mask_channels()
+    H, W, B = 24, 40, 2
+    Lo, yt, yp = _synth_batch(nb, "R", H, W, B, 10)
+    assert Lo.Cp == Ccn
+    rng = np.random.default_rng(78)
+    ct, cp = ml.depth_offset["y_true"][1], ml.depth_offset["y_pred"][1]
+    wide_t = rng.normal(0, 1, (B, H, W, ct)).astype(np.float32)
+    wide_p = rng.normal(0, 1, (B, H, W, cp)).astype(np.float16)
+    wide_t[..., :Ccn + 1] = yt
+    wide_p[..., :Ccn] = yp.astype(np.float16)
+    v = float(ml.calc_centernet(torch.from_numpy(wide_t), torch.from_numpy(wide_p.astype(np.float32))))
+    return dict(y_true=wide_t, y_pred=wide_p, nb_classes=nb, cn_channels=Ccn, total=np.float64(v),
+                cn_offset_true=np.array(ml.cn_offset["y_true"]), cn_offset_pred=np.array(ml.cn_offset["y_pred"]),
+                semseg_offset_pred=np.array(ml.semseg_offset["y_pred"]), depth_offset_pred=np.array(ml.depth_offset["y_pred"]))
+
+
 def main():
     r = ref_import.load()
+    np.savez_compressed(os.path.join(HERE, "loss_fixture.npz"), **gen_loss_fixture(r))
+    np.savez_compressed(os.path.join(HERE, "loss_maps.npz"), **gen_loss_maps(r))
+    np.savez_compressed(os.path.join(HERE, "loss_multitask.npz"), **gen_loss_multitask(r))
     np.savez_compressed(os.path.join(HERE, "render_process_a.npz"), **gen_render_process(r, 11, 14, 192, 96))
     np.savez_compressed(os.path.join(HERE, "render_process_b.npz"), **gen_render_process(r, 12, 40, 256, 128))
     np.savez_compressed(os.path.join(HERE, "render_process_empty.npz"), **gen_render_process(r, 13, 0, 64, 32))

@@ -270,3 +270,42 @@ def test_targets_above_one_are_masked(cuda):
     out = ops.loss_finalize(layout_from_params(p), ops.loss_partials(layout_from_params(p), torch.from_numpy(yt).to(cuda),
                                                                      torch.from_numpy(data["y_pred"]).to(cuda), True))
     assert float(out[0]) == pytest.approx(loss_np.total_loss(Lo, yt, data["y_pred"])[0], rel=RTOL)
+
+
+# ---- against values produced by EXECUTING the reference's loss source (tests/golden/loss_*.npz) -----------------------
+import loss_golden  # noqa: E402
+
+_GOLD = {c[0]: c for c in loss_golden.cases()}
+
+
+@pytest.mark.parametrize("name", loss_golden.case_ids())
+def test_cuda_loss_vs_executed_reference(cuda, name):
+    """CUDA path (through the drop-in mirror and the C ABI) against the unmodified reference loss.py / centertracker
+    loss.py run over oracle/tf_shim.py (make_golden.py): total, weighted focal, metric-mode focal and every field term."""
+    _, kw, yt, yp, vals = _GOLD[name]
+    H, W = yt.shape[1], yt.shape[2]
+    loss = _loss_cls(kw.get("track", False))(loss_golden.product_params(kw, H, W))
+    yt_d, yp_d = torch.from_numpy(yt).to(cuda), torch.from_numpy(yp).to(cuda)
+    assert float(loss(yt_d, yp_d)) == pytest.approx(vals["total"], rel=RTOL, abs=1e-7)
+    assert float(loss.obj_focal_loss(yt_d[..., :-1], yp_d, yt_d[..., -1])) == pytest.approx(vals["focal_weighted"], rel=RTOL, abs=1e-7)
+    assert float(loss.obj_focal_loss(yt_d, yp_d)) == pytest.approx(vals["focal_metric"], rel=RTOL, abs=1e-7)
+    for term in vals:
+        if term in ("total", "focal_weighted", "focal_metric"):
+            continue
+        got = float(getattr(loss, term + "_loss")(yt_d[..., :-1], yp_d))
+        assert got == pytest.approx(vals[term], rel=RTOL, abs=1e-7), term
+
+
+def test_cuda_multitask_vs_executed_reference(cuda, golden_dir):
+    """MultitaskLoss.calc_centernet on the wide tensors (strided in-place read) against the reference's own
+    MultitaskLoss.calc_centernet (models/multitask/loss.py:44-47) run over the shim."""
+    from cvmhot.models.multitask import MultitaskParams, MultitaskLoss
+    z = np.load(golden_dir + "/loss_multitask.npz")
+    yt, yp = z["y_true"], z["y_pred"].astype(np.float32)
+    mp = MultitaskParams(int(z["nb_classes"]))
+    mp.cn_params.INPUT_HEIGHT, mp.cn_params.INPUT_WIDTH = yt.shape[1] * 2, yt.shape[2] * 2
+    ml = MultitaskLoss(mp)
+    assert ml.cn_offset["y_true"] == list(z["cn_offset_true"]) and ml.cn_offset["y_pred"] == list(z["cn_offset_pred"])
+    assert ml.semseg_offset["y_pred"] == list(z["semseg_offset_pred"]) and ml.depth_offset["y_pred"] == list(z["depth_offset_pred"])
+    got = float(ml.calc_centernet(torch.from_numpy(yt).to(cuda), torch.from_numpy(yp).to(cuda)))
+    assert got == pytest.approx(float(z["total"]), rel=RTOL)
