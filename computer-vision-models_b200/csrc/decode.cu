@@ -922,6 +922,7 @@ struct MergeParams {
     int spi, grid, max_segs, seg_keys;
     long long n_steps;
     int off_roff, off_box, off_track;
+    int off_class, nb_classes;    // Profile R (hm == 1 + class-logit field): cls = first argmax of the logits
     float R;
     const cvm_roi* rois;
     const unsigned long long* keys;
@@ -1013,6 +1014,17 @@ __global__ void __launch_bounds__(kMergeThreads) decode_merge_kernel(const Merge
             cl = (int)(fl - pix * hm);
             const int y = (int)(pix / W), x = (int)(pix - (long long)y * W);
             const float* px = p.yp + (((size_t)b * p.H + y) * W + x) * p.stride;
+            if (hm == 1 && p.off_class >= 0) {   // np.argmax of the class logits: first maximum (post_processing.py:39-41)
+                float best = px[p.off_class];
+                cl = 0;
+                for (int k = 1; k < p.nb_classes; ++k) {
+                    const float v = px[p.off_class + k];
+                    if (v > best) {
+                        best = v;
+                        cl = k;
+                    }
+                }
+            }
             float dx = 0.f, dy = 0.f, w = 0.f, h = 0.f;
             if (p.off_roff >= 0) {
                 dx = px[p.off_roff];
@@ -1028,8 +1040,10 @@ __global__ void __launch_bounds__(kMergeThreads) decode_merge_kernel(const Merge
             bw = __fmul_rn(w, roi.inv_scale);
             bh = __fmul_rn(h, roi.inv_scale);
             if (p.off_track >= 0) {
-                tx = __fadd_rn(cx, __fmul_rn(px[p.off_track], roi.inv_scale));
-                ty = __fadd_rn(cy, __fmul_rn(px[p.off_track + 1], roi.inv_scale));
+                // the tracking OFFSET in roi coordinates: centers + track = predicted centre in the previous frame
+                // (targets: prev centre - centre, centertracker/processor.py:82-89), what cvm_track_associate consumes
+                tx = __fmul_rn(px[p.off_track], roi.inv_scale);
+                ty = __fmul_rn(px[p.off_track + 1], roi.inv_scale);
             }
         }
         p.cls[o] = cl;
@@ -1231,6 +1245,8 @@ extern "C" int cvm_decode_topk(const cvm_layout* L, const float* y_pred, int pre
     m.off_roff = L->off_roff;
     m.off_box = L->off_box;
     m.off_track = track ? L->off_track : -1;
+    m.off_class = L->off_class;
+    m.nb_classes = L->nb_classes;
     m.R = (float)L->R;
     m.rois = rois;
     m.keys = p.keys;

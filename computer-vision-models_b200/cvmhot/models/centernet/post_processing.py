@@ -16,14 +16,20 @@ def _roi_tuple(roi):
 
 
 def process_2d_output(output_mask, roi, params, min_conf_value=0.25, max_objects=512):
-    """output_mask: [H,W,C] numpy array or CUDA tensor of ONE image (no batch dim, like the reference)."""
+    """output_mask: [H,W,C] numpy array or CUDA tensor of ONE image (no batch dim, like the reference).
+    `max_objects` only sizes the first attempt; if the map holds more peaks the decode runs again with room for all of
+    them (the reference returns every peak).  The map is read as fp32 (what the network emits); box math is fp32
+    op-for-op, which equals the reference under NumPy >= 2 scalar promotion (python float * np.float32 -> float32;
+    legacy NumPy < 2 promoted to float64 there, see tests/golden/README)."""
     is_np = not isinstance(output_mask, torch.Tensor)
     x = torch.from_numpy(np.ascontiguousarray(output_mask, dtype=np.float32)).cuda() if is_np else output_mask
     H, W = int(x.shape[0]), int(x.shape[1])
     L = layout_from_params(params, H=H, W=W)
-    out = ops.decode_window9(L, x.unsqueeze(0), min_conf=min_conf_value, rois_dev=ops.make_rois([_roi_tuple(roi)], x.device),
-                             max_out=max_objects)
-    n = min(int(out["counts"][0].item()), max_objects)
+    rois_dev = ops.make_rois([_roi_tuple(roi)], x.device)
+    out = ops.decode_window9(L, x.unsqueeze(0), min_conf=min_conf_value, rois_dev=rois_dev, max_out=max_objects)
+    n = int(out["counts"][0].item())
+    if n > max_objects:       # the reference returns EVERY peak: run again with room for all of them
+        out = ops.decode_window9(L, x.unsqueeze(0), min_conf=min_conf_value, rois_dev=rois_dev, max_out=n)
     cls = out["cls"][0, :n].cpu().numpy()
     centers = out["centers"][0, :n].cpu().numpy()
     boxes = out["boxes"][0, :n].cpu().numpy()

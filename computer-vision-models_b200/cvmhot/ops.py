@@ -126,6 +126,9 @@ def render_prev_heatmap(layout: Layout, objs_dev, obj_offsets_dev, B, out=None):
     _need_cuda(obj_offsets_dev, "obj_offsets", torch.int32)
     if out is None:
         out = torch.empty((B, layout.H, layout.W, 1), dtype=torch.float32, device=objs_dev.device)
+    _need_cuda(out, "out", torch.float32)
+    if out.numel() != B * layout.H * layout.W or not out.is_contiguous():
+        raise _lib.CvmError("out must be a contiguous [B,H,W,1] tensor")
     s = layout.c_struct()
     rc = _lib.lib().cvm_render_prev_hm(C.byref(s), _ptr(objs_dev), _ptr(obj_offsets_dev), B, _ptr(out), _stream())
     _lib.check(rc, "cvm_render_prev_hm")
@@ -135,7 +138,24 @@ def render_prev_heatmap(layout: Layout, objs_dev, obj_offsets_dev, B, out=None):
 def fill_heatmap_inplace(objs_dev, n_obj, heat, weights, H, W, R, alpha):
     """max/min-combine records into existing planes: heat [H,W,C] (channel 0 of the given view) and weights [H,W] or None."""
     _need_cuda(heat, "heat", torch.float32)
-    hs = int(heat.stride(-2)) if heat.dim() == 3 else 1
+    _need_cuda(objs_dev, "objs")
+    H, W = int(H), int(W)
+    if heat.dim() == 3:       # [H,W,C] view: channel 0 of the given view, rows must be dense in pixels
+        hs = int(heat.stride(-2))
+        if tuple(heat.shape[:2]) != (H, W) or heat.stride(0) != W * hs or heat.stride(-1) != 1:
+            raise _lib.CvmError("heat must be a [H,W,C] view with stride(0) == W*stride(1) and dense channels")
+    elif heat.dim() == 2:
+        hs = 1
+        if tuple(heat.shape) != (H, W) or not heat.is_contiguous():
+            raise _lib.CvmError("heat must be a contiguous [H,W] plane")
+    else:
+        raise _lib.CvmError("heat must be [H,W] or [H,W,C]")
+    if weights is not None:
+        _need_cuda(weights, "weights", torch.float32)
+        if tuple(weights.shape) != (H, W) or not weights.is_contiguous():
+            raise _lib.CvmError("weights must be a contiguous float32 [H,W] plane")
+    if objs_dev.numel() < int(n_obj) * OBJ_DTYPE.itemsize:
+        raise _lib.CvmError("objs holds fewer than n_obj records")
     rc = _lib.lib().cvm_fill_heatmap_inplace(_ptr(objs_dev), int(n_obj), _ptr(heat), hs, _ptr(weights), int(H), int(W),
                                              float(R), float(alpha), _stream())
     _lib.check(rc, "cvm_fill_heatmap_inplace")

@@ -148,8 +148,9 @@ int cvm_loss_bwd(const cvm_layout* L, const float* y_true, int y_true_stride, co
 /* ---- decode -------------------------------------------------------------------------------------------------- */
 size_t cvm_decode_topk_workspace_bytes(const cvm_layout* L, int pred_stride, int B, int K);   /* 0 = unsupported shape */
 /* y_pred [B,H,W,pred_stride] (pred_stride >= Cp).  Outputs (device): scores[B,K] f32, cls[B,K] i32,
- * flat[B,K] i64 (NHWC flat index (y*W+x)*hm+c), centers[B,K,2], boxes[B,K,4] (tlx,tly,w,h), track[B,K,2] (previous
- * centre; may be NULL).  Order: score desc, ties by lowest flat index (tf.nn.top_k).  rois: per image or NULL. */
+ * flat[B,K] i64 (NHWC flat index (y*W+x)*hm+c), centers[B,K,2], boxes[B,K,4] (tlx,tly,w,h), track[B,K,2] (the tracking
+ * OFFSET scaled to roi coordinates: centers + track = predicted centre in the previous frame, the query point of
+ * cvm_track_associate; may be NULL).  Order: score desc, ties by lowest flat index (tf.nn.top_k).  rois: per image or NULL. */
 int cvm_decode_topk(const cvm_layout* L, const float* y_pred, int pred_stride, int B, int K, const cvm_roi* rois,
                     float* scores, int32_t* cls, long long* flat, float* centers, float* boxes, float* track,
                     void* ws, size_t ws_bytes, void* stream);

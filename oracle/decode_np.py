@@ -53,7 +53,8 @@ def decode_topk_image(L: Layout, y_pred, K=100, roi=(1.0, 0, 0)):
     """One image. y_pred [H,W,Cp] f32. roi = (scale, offset_left, offset_top).
 
     returns dict(scores[K] f32, cls[K] i32, flat[K] i64, centers[K,2] f32, boxes[K,4] f32, track[K,2] f32)
-    `track` = previous-frame centre (cx + tx/scale, cy + ty/scale) when the layout has a track field.
+    `track` = tracking offset in roi coordinates (tx/scale, ty/scale) when the layout has a track field:
+    centers + track is the predicted centre in the previous frame (what oracle/track_np.py consumes).
     """
     H, W, hm = L.H, L.W, L.hm
     y_pred = np.asarray(y_pred, dtype=np.float32)
@@ -73,11 +74,13 @@ def decode_topk_image(L: Layout, y_pred, K=100, roi=(1.0, 0, 0)):
         px = y_pred[y, x]
         dx, dy = (px[L.off_roff], px[L.off_roff + 1]) if L.off_roff >= 0 else (0.0, 0.0)
         w, h = (px[L.off_box], px[L.off_box + 1]) if L.off_box >= 0 else (0.0, 0.0)
+        if hm == 1 and L.off_class >= 0:        # Profile R: class = first argmax of the class logits (post_processing.py:39-41)
+            out["cls"][i] = int(np.argmax(px[L.off_class:L.off_class + L.nb_classes]))
         cx, cy, box = box_math(x, y, dx, dy, w, h, L.R, scale, off_left, off_top)
         out["centers"][i] = (cx, cy)
         out["boxes"][i] = box
         if L.off_track >= 0:
-            out["track"][i] = (cx + px[L.off_track] * inv, cy + px[L.off_track + 1] * inv)
+            out["track"][i] = (px[L.off_track] * inv, px[L.off_track + 1] * inv)
     return out
 
 
