@@ -215,8 +215,10 @@ def loss_backward(layout: Layout, y_true, y_pred, partials, upstream=None, out=N
 
 
 # ---- decode ----------------------------------------------------------------------------------------------------------
-def decode_topk(layout: Layout, y_pred, K=100, rois_dev=None, want_track=None):
-    """Canonical CenterNet decode -> dict(scores[B,K], cls[B,K] i32, flat[B,K] i64, centers[B,K,2], boxes[B,K,4], track[B,K,2])."""
+def decode_topk(layout: Layout, y_pred, K=100, rois_dev=None, want_track=None, semseg=None):
+    """Canonical CenterNet decode -> dict(scores[B,K], cls[B,K] i32, flat[B,K] i64, centers[B,K,2], boxes[B,K,4], track[B,K,2]).
+    semseg=(off, n_cls): also take the per-pixel argmax of channels [off, off+n_cls) of the same tensor in the same pass
+    (multitask head) -> out["semseg_ids"] uint8 [B,H,W]."""
     st = _pixel_strided(y_pred, "y_pred")
     if y_pred.dim() != 4 or y_pred.shape[1] != layout.H or y_pred.shape[2] != layout.W:
         raise _lib.CvmError("y_pred must be [B,H,W,C] with the layout's H,W")
@@ -235,10 +237,19 @@ def decode_topk(layout: Layout, y_pred, K=100, rois_dev=None, want_track=None):
     if nbytes == 0 and B > 0:
         raise _lib.CvmError("cvm_decode_topk: unsupported shape: " + _lib.lib().cvm_last_error().decode())
     ws = _workspace(dev, nbytes, "decode")
-    rc = _lib.lib().cvm_decode_topk(C.byref(s), _ptr(y_pred), st, B, K, _ptr(rois_dev), _ptr(out["scores"]),
-                                    _ptr(out["cls"]), _ptr(out["flat"]), _ptr(out["centers"]), _ptr(out["boxes"]),
-                                    _ptr(out["track"]), _ptr(ws), ws.numel(), _stream())
-    _lib.check(rc, "cvm_decode_topk")
+    if semseg is None:
+        rc = _lib.lib().cvm_decode_topk(C.byref(s), _ptr(y_pred), st, B, K, _ptr(rois_dev), _ptr(out["scores"]),
+                                        _ptr(out["cls"]), _ptr(out["flat"]), _ptr(out["centers"]), _ptr(out["boxes"]),
+                                        _ptr(out["track"]), _ptr(ws), ws.numel(), _stream())
+        _lib.check(rc, "cvm_decode_topk")
+    else:
+        off, n_cls = int(semseg[0]), int(semseg[1])
+        out["semseg_ids"] = torch.empty((B, layout.H, layout.W), dtype=torch.uint8, device=dev)
+        rc = _lib.lib().cvm_decode_topk_semseg(C.byref(s), _ptr(y_pred), st, B, K, _ptr(rois_dev), _ptr(out["scores"]),
+                                               _ptr(out["cls"]), _ptr(out["flat"]), _ptr(out["centers"]), _ptr(out["boxes"]),
+                                               _ptr(out["track"]), off, n_cls, _ptr(out["semseg_ids"]), _ptr(ws), ws.numel(),
+                                               _stream())
+        _lib.check(rc, "cvm_decode_topk_semseg")
     return out
 
 

@@ -155,6 +155,14 @@ int cvm_decode_topk(const cvm_layout* L, const float* y_pred, int pred_stride, i
                     float* scores, int32_t* cls, long long* flat, float* centers, float* boxes, float* track,
                     void* ws, size_t ws_bytes, void* stream);
 
+/* cvm_decode_topk plus, in the SAME pass over y_pred, the per-pixel class pick of a semseg slice that lives in the same
+ * tensor (multitask head: models/multitask/loss.py:21-32 slices, multitask/callbacks.py:107-110 + to_3channel's np.argmax,
+ * common/utils/image.py:88: first maximum of channels [seg_off, seg_off + seg_n)).  seg_ids: u8 [B,H,W] class ids
+ * (what cvm_semseg_argmax mode 0 writes).  The wide tensor is read once instead of twice. */
+int cvm_decode_topk_semseg(const cvm_layout* L, const float* y_pred, int pred_stride, int B, int K, const cvm_roi* rois,
+                           float* scores, int32_t* cls, long long* flat, float* centers, float* boxes, float* track,
+                           int seg_off, int seg_n, unsigned char* seg_ids, void* ws, size_t ws_bytes, void* stream);
+
 /* Profile R: window x window first-argmax (window odd, 9 in the reference) + strict threshold, scan order.
  * counts[B] = number of objects found (may exceed max_out; only the first max_out in scan order are written). */
 size_t cvm_decode_window9_workspace_bytes(const cvm_layout* L, int B);

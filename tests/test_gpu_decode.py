@@ -142,6 +142,48 @@ def test_topk_multitask_wide_map(cuda):
     _check_topk(out, ref, 100)
     ids = class_ids(wide_d, 14, 5).cpu().numpy()
     assert np.array_equal(ids, image_np.class_ids(wide[..., 14:19], 5))
+    # the same two results from ONE pass over the wide tensor (cvm_decode_topk_semseg)
+    wide[0, 3, 7, 14:19] = 0.25                        # all equal -> first index; a NaN is never "greater"
+    wide[1, 5, 9, 14:19] = [0.1, np.nan, 0.3, 0.3, -1.0]
+    wide_d = torch.from_numpy(wide).to(cuda)
+    fused = ops.decode_topk(layout_from_params(_params(C, True, H, W)), wide_d[..., :Lo.Cp], K=100, semseg=(14, 5))
+    _check_topk(fused, ref, 100)
+    assert np.array_equal(fused["semseg_ids"].cpu().numpy(), class_ids(wide_d, 14, 5).cpu().numpy())
+    assert fused["semseg_ids"][0, 3, 7] == 0 and fused["semseg_ids"][1, 5, 9] == 2
+
+
+def test_topk_semseg_fused_generic_layout(cuda):
+    """fused argmax on a layout without a compile-time instantiation (7 heatmap channels, 17-float pixels, odd sizes)."""
+    from cvmhot import ops
+    from cvmhot.layout import layout_from_params
+    from cvmhot.common.utils.image import class_ids
+    H, W, C, B = 37, 53, 7, 3
+    Lo = make_layout(H, W, C, "N")
+    data = synth.make_batch(Lo, 10, B)
+    rng = np.random.default_rng(4)
+    wide = rng.normal(0, 1, (B, H, W, 17)).astype(np.float32)
+    wide[..., :Lo.Cp] = data["y_pred"]
+    wide_d = torch.from_numpy(wide).to(cuda)
+    ref = decode_np.decode_topk(Lo, data["y_pred"], 60)
+    out = ops.decode_topk(layout_from_params(_params(C, True, H, W)), wide_d[..., :Lo.Cp], K=60, semseg=(Lo.Cp, 6))
+    _check_topk(out, ref, 60)
+    assert np.array_equal(out["semseg_ids"].cpu().numpy(), np.argmax(wide[..., Lo.Cp:Lo.Cp + 6], axis=-1).astype(np.uint8))
+
+
+def test_topk_profile_r_class_from_logits(cuda):
+    """Profile R (one objectness channel + class-logit field, the reference's default params): cls = first argmax of the
+    class logits at the peak, like process_2d_output (post_processing.py:39-41), not flat % hm."""
+    from cvmhot.models.centernet.post_processing import decode_topk
+    H, W, nb, B = 40, 57, 6, 3
+    Lo = make_layout(H, W, nb, "R")
+    data = synth.make_batch(Lo, 12, B)
+    yp = data["y_pred"]
+    yp[0, 5, 5, 0] = 0.999
+    yp[0, 5, 5, Lo.off_class:Lo.off_class + nb] = [0.5, 2.0, 2.0, -1.0, 0.0, 1.0]    # tie -> first
+    ref = decode_np.decode_topk(Lo, yp, 50)
+    out = decode_topk(torch.from_numpy(yp).to(cuda), _params(nb, False, H, W), K=50)
+    _check_topk(out, ref, 50)
+    assert ref["cls"].max() > 0 and int(out["cls"][0, 0]) == 1
 
 
 @pytest.mark.parametrize("H,W,K_cls,B", [(40, 64, 40, 2), (33, 35, 3, 3)])

@@ -154,3 +154,44 @@ def _run_tracker_sequence(cuda):
     assert np.array_equal(seen[1], seen[0])
     assert np.array_equal(seen[2][:, :n], seen[0])
     assert (seen[2][:, n] == n + 1).all()
+
+
+@pytest.mark.gpu
+def test_decode_to_tracker_pipeline(cuda):
+    """The documented usage end to end: decode_topk of a CenterTracker layout -> Tracker.step over three frames.  Objects
+    move by a known velocity, the track_offset head predicts (previous centre - centre) in input px as the processor
+    scatters it (centertracker/processor.py:82-89): ids must survive, `centers + track` must land on the previous centres."""
+    from cvmhot.models.centertracker import CentertrackerParams, Tracker
+    from cvmhot.models.centernet.post_processing import decode_topk
+    H, W, nb, B, n = 64, 96, 4, 2, 5
+    p = CentertrackerParams(nb, True)
+    p.INPUT_HEIGHT, p.INPUT_WIDTH = H * 2, W * 2
+    from cvmhot.layout import layout_from_params
+    L = layout_from_params(p)
+    rng = np.random.default_rng(8)
+    pos = np.stack([np.stack([np.linspace(12, W - 12, n), rng.uniform(12, H - 12, n)], 1) for _ in range(B)])   # mask px
+    vel = rng.integers(-2, 3, (B, n, 2)).astype(np.float64)
+    cls = rng.integers(0, nb, (B, n))
+    tracker = Tracker(min_score=0.1, new_thresh=0.3)
+    all_ids, prev_centres = [], None
+    for f in range(3):
+        yp = np.zeros((B, H, W, L.Cp), np.float32)
+        yp[..., :nb] = 0.01
+        cur = pos + vel * f
+        for b in range(B):
+            for i in range(n):
+                x, y = int(cur[b, i, 0]), int(cur[b, i, 1])
+                yp[b, y, x, cls[b, i]] = 0.9 - 0.05 * i
+                yp[b, y, x, L.off_roff:L.off_roff + 2] = 0.0
+                yp[b, y, x, L.off_box:L.off_box + 2] = 16.0
+                yp[b, y, x, L.off_track:L.off_track + 2] = -vel[b, i] * 2.0      # input px (R = 2)
+        det = decode_topk(torch.from_numpy(yp).to(cuda), p, K=16)
+        ids = tracker.step(det).cpu().numpy()
+        centres = det["centers"].cpu().numpy()[:, :n]
+        if prev_centres is not None:
+            q = centres + det["track"].cpu().numpy()[:, :n]
+            assert np.allclose(q, prev_centres)                                   # offset convention: centre + track = previous centre
+        prev_centres = centres
+        assert (ids[:, :n] > 0).all() and (ids[:, n:] == 0).all()
+        all_ids.append(ids[:, :n].copy())
+    assert np.array_equal(all_ids[0], all_ids[1]) and np.array_equal(all_ids[1], all_ids[2])

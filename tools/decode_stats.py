@@ -1,4 +1,4 @@
-"""Per-warp cycle breakdown of decode_scan_kernel (needs a build with EXTRA=-DCVM_DECODE_STATS)."""
+"""Per-role cycle breakdown of decode_scan_kernel (needs a build with `make EXTRA=-DCVM_DECODE_STATS`, never the shipped one)."""
 import ctypes as C, os, sys
 sys.path.insert(0, "/root/repo/computer-vision-models_b200"); sys.path.insert(0, "/root/repo")
 import torch
@@ -14,14 +14,15 @@ yp = torch.empty((B, H, W, L.Cp), device=dev)
 yp[..., :Cc] = torch.sigmoid(torch.randn((B, H, W, Cc), device=dev, generator=g) * 1.5 - 4.0)
 yp[..., Cc:] = torch.rand((B, H, W, L.Cp - Cc), device=dev, generator=g) * 40
 lib = _lib.lib()
-out = (C.c_ulonglong * 16)()
+out = (C.c_ulonglong * 32)()
 ops.decode_topk(L, yp, K=100)
 lib.cvm_decode_stats(out, 1)
 ops.decode_topk(L, yp, K=100)
 lib.cvm_decode_stats(out, 1)
 v = list(out)
-ws = v[6]
-names = ["wait cycles", "scan cycles", "test_hits cycles (threshold set)", "tail (release/threshold/gather) cycles", "pixel hits", "test rounds", "warp-steps", "test_hits cycles (no threshold yet)", "append calls", "-", "gather cycles (segment end)", "gather calls (segment end, per warp)", "append: count atomic + shuffles", "append: key / histogram stores", "append: syncwarp + flag vote", "append: rescan"]
+n_cta = 148
+names = ["scanner: wait full barrier", "scanner: wait first threshold (hint owner)", "scanner: wait segment threshold", "scanner: wait flush",
+         "scanner: queue back-pressure (lane cycles)", "scanner: total", "tester: idle", "tester: test_records", "tester: total", "records",
+         "batches", "test rounds", "peaks appended", "loader: wait free slot", "loader: total", "tester: gather at segment end"]
 for n, x in zip(names, v):
-    print(f"{n:45s} {x:14d}  per warp-step {x / max(ws, 1):10.1f}")
-print("pixel hits per image", v[4] / B)
+    print(f"{n:48s} {x:16d}  per CTA {x / n_cta:14.1f}")
