@@ -44,10 +44,10 @@ constexpr int kLoaderWarp = kTestWarps + kScanWarps;
 constexpr int kThreads = (kLoaderWarp + 1) * 32;
 constexpr int kMergeThreads = 256;
 constexpr int kMaxSlots = kScanWarps;   // ring depth (granules): one slot per active scanner warp
-constexpr int kMaxT = 512;         // pixels per granule
+constexpr int kMaxT = 1024;        // pixels per granule (a scanner lane keeps one hit bit per pixel of its granule: 32 x 32)
 constexpr int kGranBytes = 32768;  // target granule size
 constexpr int kUnroll = 4;         // pixels per scanner lane and iteration
-constexpr int kQShift = 8;
+constexpr int kQShift = 7;
 constexpr int kQCap = 1 << kQShift;   // records per queue (one queue per tester warp and segment parity)
 constexpr int kSlack = 1536;       // buffer entries beyond K before the (rare) fallback compaction
 constexpr int kSegKeys = 512;      // keys a segment may publish without an exact select (the merge kernel selects anyway)
@@ -58,8 +58,11 @@ constexpr int kMergeCap = 4096;    // merge kernel: keys buffered before an inte
 constexpr int kSmemBudget = 227 * 1024 - 1024;
 constexpr unsigned kFull = 0xffffffffu;
 
-// queue records: lo = lap bit | marker bit | upper-half bit | pixel index (or marker code), hi = channel mask
-constexpr unsigned kRecMarker = 1u << 30, kRecUpper = 1u << 29, kRecPixel = (1u << 29) - 1u;
+// queue records: lo = lap bit | marker bit | pixel index (or marker code), hi = kind of record
+constexpr unsigned kRecMarker = 1u << 30, kRecPixel = (1u << 30) - 1u;
+constexpr unsigned kKindAll = 1u;      // test every channel of the pixel that reaches the threshold
+constexpr unsigned kKindHint = 2u;     // hint: test the pixel's best channel only
+constexpr unsigned kKindRest = 3u;     // second pass over a hinted granule: like kKindAll without the channel a hint covered
 constexpr unsigned kMarkEnd = 1u, kMarkHintEnd = 2u;
 
 struct DecodeParams {
@@ -80,6 +83,11 @@ struct DecodeParams {
     unsigned long long* keys;     // [grid][max_segs][seg_keys]
     int* counts;                  // [grid][max_segs]
     int rescan_step;              // appends after which the score histogram is scanned again
+    unsigned int thr0_bits;       // threshold a segment starts with (0: none, bootstrap with hints)
+    int ring;                     // 1: the 3x3 neighbours of a record are read from the ring (granules stay resident until the
+                                  // records of their neighbourhood are tested); 0: from global memory (maps too wide for that)
+    int hg;                       // ring mode: granules of history / lookahead that hold a pixel's 3x3 neighbourhood
+    float inv_T, inv_W;           // 1 / T, 1 / W
     unsigned char* seg_out;       // fused semseg argmax: class ids [B*H*W] (NULL: off)
     int seg_off, seg_n;           // channels [seg_off, seg_off + seg_n) of every pixel
 };
@@ -92,6 +100,7 @@ struct SharedHead {
     unsigned int hist[256];       // radix select
     int misc[4];
     unsigned int thr_bits[2];     // per segment parity: running threshold score (float bits); 0 = not established (hint phase)
+    float hint_guess[2];          // pixels whose maximum reaches this were hinted (first granule of the segment)
     int hint_done[2];             // tester warps that have seen the end of the segment's hints
     int flushed;                  // segments published so far
     int cur_par;                  // parity of the segment the testers are working on
@@ -101,6 +110,15 @@ struct SharedHead {
     int maxbin;                   // highest score bin seen so far
     int seg_done;                 // tester warps that finished the current segment
     unsigned long long thr;       // K-th key of the last exact select
+    // ring mode, per slot (sequence numbers are 1 + the index of the granule in this CTA's load order, so 0 = never)
+    int landed_seq[kMaxSlots];    // the slot's tenant has arrived (set by the owning scanner warp)
+    int scan_seq[kMaxSlots];      // ... and has been scanned: `pushed` is final
+    int pushed[kMaxSlots];        // records pushed for the tenant
+    int tested[kMaxSlots];        // records of the tenant the testers are done with
+#ifdef CVM_DECODE_STATS
+    unsigned long long stats[kThreads / 32][24];   // private to each warp's lane 0: plain adds
+    int roles_done;
+#endif
     unsigned int q_tail[kTestWarps][2];   // records reserved (producers)
     unsigned int q_head[kTestWarps][2];   // records consumed (tester), for back-pressure
 };
@@ -136,6 +154,15 @@ size_t smem_bytes(int S, int gran_floats, int cap, int K) {
     return (size_t)kHeadBytes + ring_bytes_of(S, gran_floats) + kQueueBytes + (size_t)cap * 8 + (size_t)K * 8 + (size_t)kScoreBins * 4;
 }
 
+// Ordering between the warps of the CTA.  All flags, counters and queue records live in shared memory and are accessed with
+// volatile loads / stores or atomics, which the SM performs in each warp's program order; a consumer only acts on a value
+// after it has read the flag that guards it (a control dependency).  fence_cta() (acquire-release at CTA scope) is kept at
+// the rare hand-over points; order_only() just stops the compiler from moving accesses.  (__threadfence_block() compiles
+// to MEMBAR.SC.CTA, a sequentially consistent fence that waits out everything the thread has in flight: thousands of
+// cycles per call next to a saturated memory system.)
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+__device__ __forceinline__ void order_only() { asm volatile("" ::: "memory"); }
+
 __device__ __forceinline__ unsigned ld_vol(const unsigned* p) { return *(volatile const unsigned*)p; }
 __device__ __forceinline__ int ld_vol(const int* p) { return *(volatile const int*)p; }
 
@@ -159,12 +186,32 @@ __device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity
 #ifdef CVM_DECODE_STATS
 __device__ unsigned long long g_decode_stats[32];
 #define STAT_T0() const long long st_t0_ = clock64()
-#define STAT_ACC(i) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_decode_stats[i], (unsigned long long)(clock64() - st_t0_)); } while (0)
-#define STAT_ADD(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_decode_stats[i], (unsigned long long)(v)); } while (0)
+#define STAT_LAP(i) do { const long long t_ = clock64(); if ((threadIdx.x & 31) == 0) sm_head()->stats[threadIdx.x >> 5][i] += (unsigned long long)(t_ - st_lap_); st_lap_ = t_; } while (0)
+#define STAT_LAP0() long long st_lap_ = clock64()
+// (accumulated in shared memory, flushed to the global array by the last warp of the CTA to finish: global atomics inside the
+// polling loops would disturb what is being measured)
+#define STAT_ACC(i) do { if ((threadIdx.x & 31) == 0) sm_head()->stats[threadIdx.x >> 5][i] += (unsigned long long)(clock64() - st_t0_); } while (0)
+#define STAT_ADD(i, v) do { if ((threadIdx.x & 31) == 0) sm_head()->stats[threadIdx.x >> 5][i] += (unsigned long long)(v); } while (0)
 #else
 #define STAT_T0() ((void)0)
+#define STAT_LAP(i) ((void)0)
+#define STAT_LAP0() ((void)0)
 #define STAT_ACC(i) ((void)0)
 #define STAT_ADD(i, v) ((void)0)
+#endif
+
+#ifdef CVM_DECODE_STATS
+__device__ __noinline__ void stats_role_done(const DecodeParams& p) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        __threadfence_block();
+        if (atomicAdd(&sm_head()->roles_done, 1) == kTestWarps + p.S) {
+            __threadfence_block();
+            for (int w = 0; w < kThreads / 32; ++w)
+                for (int k = 0; k < 24; ++k) atomicAdd(&g_decode_stats[k], sm_head()->stats[w][k]);
+        }
+    }
+}
 #endif
 
 // named barrier over the first `nt` threads of the CTA (the tester warps; scanners and loader never join)
@@ -346,14 +393,14 @@ __device__ __noinline__ void flush_segment(const DecodeParams& p, int seg) {
         p.counts[o] = n;
         h->count = 0;
         h->thr = 0ull;
-        h->thr_bits[par] = 0u;      // the parity is reused by segment seg + 2: back to the hint phase
+        h->thr_bits[par] = p.thr0_bits;   // the parity is reused by segment seg + 2: back to the hint phase
         h->hint_done[par] = 0;
         h->cur_par = par ^ 1;
         h->scanned = 0;
         h->maxbin = 0;
         h->compact_flag = 0;
         h->seg_done = 0;
-        __threadfence_block();
+        fence_cta();
         *(volatile int*)&h->flushed = seg + 1;   // scanners waiting to enter segment seg + 2 go on
     }
     group_sync(nt);
@@ -445,24 +492,8 @@ __device__ __forceinline__ void q_wait_space(SharedHead* h, int t, int par, unsi
         SPIN_GUARD(spins, "queue back-pressure");
     }
 #ifdef CVM_DECODE_STATS
-    atomicAdd(&g_decode_stats[4], (unsigned long long)(clock64() - st_t0_));   // (per waiting lane)
+    h->stats[threadIdx.x >> 5][4 + (threadIdx.x & 31 ? 16 : 0)] += (unsigned long long)(clock64() - st_t0_);   // (lane 0: pushes; others: markers)
 #endif
-}
-
-// warp-collective: lanes with `has` push (lo, hi) to queue (t, par)
-__device__ __forceinline__ void q_push(const DecodeParams& p, int t, int par, bool has, unsigned lo, unsigned hi) {
-    const unsigned bal = __ballot_sync(kFull, has);
-    if (!bal) return;
-    SharedHead* h = sm_head();
-    const int lane = threadIdx.x & 31, n = __popc(bal);
-    unsigned pos = 0;
-    if (lane == 0) {
-        pos = atomicAdd(&h->q_tail[t][par], (unsigned)n);
-        q_wait_space(h, t, par, pos + (unsigned)n);
-    }
-    pos = __shfl_sync(kFull, pos, 0);
-    __threadfence_block();   // the consumer's reads of the old tenants happened before its head update that we saw
-    if (has) q_store(sm_queue(p, t, par), pos + __popc(bal & ((1u << lane) - 1u)), lo, hi);
 }
 
 // one marker record to every tester queue of the parity (lane t serves queue t)
@@ -473,7 +504,7 @@ __device__ __forceinline__ void q_push_marker(const DecodeParams& p, int par, un
     if (lane < kTestWarps) {
         const unsigned pos = atomicAdd(&h->q_tail[lane][par], 1u);
         q_wait_space(h, lane, par, pos + 1u);
-        __threadfence_block();
+        order_only();
         q_store(sm_queue(p, lane, par), pos, kRecMarker | code, 0u);
     }
     __syncwarp();
@@ -491,33 +522,28 @@ __device__ __forceinline__ void wait_flushed(SharedHead* h, int want) {
     STAT_ACC(3);
 }
 
-// MODE 0: push every (pixel, channels >= threshold).  MODE 1 (hints): push the best channel of the pixels whose maximum
-// reaches `guess`.  MODE 2 (second pass over the hinted granule): like 0 without the channels pushed as hints.
-template <int STRIDE, int HM, bool SEG, int MODE>
-__device__ __forceinline__ void scan_granule(const DecodeParams& p, const float* gran, int npx, int q0, long long img, int par,
-                                             float guess, unsigned& rr) {
-    using M = mask_t<HM>;
-    SharedHead* h = sm_head();
+// Scan of one granule: bit j of the result = pixel (j / kUnroll) * 32 * kUnroll + (j % kUnroll) * 32 + lane of the granule has
+// a heatmap channel that reaches thr_f.  Nothing else happens per pixel: which channels, and whether they are peaks, is the
+// testers' business.  ARGMAX: also write the class id of the pixel's semseg slice.
+template <int STRIDE, int HM, bool ARGMAX>
+__device__ __forceinline__ unsigned scan_granule(const DecodeParams& p, const float* gran, int npx, int q0, long long img, float thr_f) {
     const int lane = threadIdx.x & 31;
     const int stride = STRIDE ? STRIDE : p.stride, hm = HM ? HM : p.hm;
-    for (int base = 0; base < npx; base += 32 * kUnroll) {
-        const float thr_f = MODE == 1 ? guess : __uint_as_float(ld_vol(&h->thr_bits[par]));
-        float vmax[kUnroll];
-        bool hit[kUnroll], any = false;
+    unsigned bits = 0u;
+    for (int base = 0, j = 0; base < npx; base += 32 * kUnroll, j += kUnroll) {
 #pragma unroll
         for (int k = 0; k < kUnroll; ++k) {
             const int pix = base + k * 32 + lane;
             const bool ok = pix < npx;
             const float* px = gran + (size_t)(ok ? pix : 0) * stride;
-            vmax[k] = pixel_max<STRIDE, HM>(px, hm);
-            hit[k] = ok && vmax[k] >= thr_f;
-            any = any || hit[k];
-            if (SEG && MODE != 2 && ok) {   // first maximum of the semseg slice (np.argmax, common/utils/image.py:88)
-                const float* s = px + p.seg_off;
+            const float vmax = pixel_max<STRIDE, HM>(px, hm);
+            bits |= (ok && vmax >= thr_f ? 1u : 0u) << (j + k);
+            if (ARGMAX && ok) {   // first maximum of the semseg slice (np.argmax, common/utils/image.py:88)
+                const float* sp = px + p.seg_off;
                 int idx = 0;
-                float best = s[0];
+                float best = sp[0];
                 for (int c = 1; c < p.seg_n; ++c) {
-                    const float v = s[c];
+                    const float v = sp[c];
                     if (v > best) {
                         best = v;
                         idx = c;
@@ -526,40 +552,53 @@ __device__ __forceinline__ void scan_granule(const DecodeParams& p, const float*
                 p.seg_out[(size_t)img * p.HW + (size_t)(q0 + pix)] = (unsigned char)idx;
             }
         }
-        if (!__any_sync(kFull, any)) continue;
+    }
+    return bits;
+}
+
+// Push one record per hit bit (see scan_granule) to the tester queues: chunks of kUnroll bits per lane (<= 32 * kUnroll
+// records, one reservation each).  spread: every chunk to the next tester (hints: many records, and the segment waits for
+// them); otherwise all to tester `rr` (a tester finds the few records of a granule together).  Returns the records pushed.
+__device__ __forceinline__ int push_hits(const DecodeParams& p, unsigned bits, int npx, int q0, int par, unsigned kind, bool spread,
+                                         unsigned& rr) {
+    SharedHead* h = sm_head();
+    const int lane = threadIdx.x & 31;
+    int n_pushed = 0;
+    if (!__any_sync(kFull, bits != 0u)) return 0;
+    for (int base = 0, j = 0; base < npx; base += 32 * kUnroll, j += kUnroll) {
+        const unsigned mine = (bits >> j) & ((1u << kUnroll) - 1u);
+        if (!__any_sync(kFull, mine != 0u)) continue;
+        // exclusive prefix of the per-lane counts
+        const int cnt = __popc(mine);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(kFull, incl, 31);
+        const int t = (int)(rr % kTestWarps);
+        if (spread) ++rr;
+        unsigned pos = 0;
+        if (lane == 0) {
+            pos = atomicAdd(&h->q_tail[t][par], (unsigned)total);
+            q_wait_space(h, t, par, pos + (unsigned)total);
+        }
+        pos = __shfl_sync(kFull, pos, 0) + (unsigned)(incl - cnt);
+        order_only();   // (the consumer's reads of the old tenants happened before its head update that lane 0 saw)
+        unsigned long long* q = sm_queue(p, t, par);
 #pragma unroll
         for (int k = 0; k < kUnroll; ++k) {
-            if (!__any_sync(kFull, hit[k])) continue;
-            const int pix = base + k * 32 + lane;
-            M m = 0;
-            if (hit[k]) {
-                const float* px = gran + (size_t)pix * stride;
-                if (MODE == 1) {
-                    const M top = channel_mask<HM>(px, hm, vmax[k]);
-                    m = top & ((M)0 - top);                  // lowest channel holding the maximum
-                } else {
-                    m = channel_mask<HM>(px, hm, thr_f);
-                    if (MODE == 2 && vmax[k] >= guess) {     // that channel went out as a hint already
-                        const M top = channel_mask<HM>(px, hm, vmax[k]);
-                        m &= ~(top & ((M)0 - top));
-                    }
-                }
-            }
-            const unsigned q = (unsigned)(q0 + pix);
-            const int t = (int)(rr % kTestWarps);
-            ++rr;
-            if (sizeof(M) == 4) {
-                q_push(p, t, par, m != 0, q, (unsigned)m);
-            } else {
-                q_push(p, t, par, (unsigned)m != 0u, q, (unsigned)m);
-                q_push(p, t, par, (unsigned)((unsigned long long)m >> 32) != 0u, q | kRecUpper, (unsigned)((unsigned long long)m >> 32));
-            }
+            if (mine & (1u << k)) q_store(q, pos++, (unsigned)(q0 + base + k * 32 + lane), kind);
         }
+        n_pushed += total;
     }
+    return n_pushed;
 }
 
 template <int STRIDE, int HM, bool SEG>
-__device__ __forceinline__ void scanner_main(const DecodeParams& p, int w, long long g_first, int n_local, long long img0, int n_segs) {
+__device__ __forceinline__ void scanner_main(const DecodeParams& p, int w, long long g_first, int n_local, int lead, int n_load,
+                                             long long img0, int n_segs) {
     SharedHead* const h = sm_head();
     const float* const ring = sm_ring();
     const int lane = threadIdx.x & 31;
@@ -568,63 +607,110 @@ __device__ __forceinline__ void scanner_main(const DecodeParams& p, int w, long 
 #ifdef CVM_DECODE_STATS
     const long long sc_t0 = clock64();
 #endif
+    const int nsw = p.S, slot = w;   // granule ls of the load order lives in slot ls % S == w: this warp's own slot
     int cur_seg = 0;              // segments [0, cur_seg) have got this warp's END marker
     unsigned rr = (unsigned)w;    // round-robin over the tester queues
-    long long img = (g_first + w) / p.gpi;
-    int gi = (int)((g_first + w) - img * p.gpi);
-    const int nsw = p.S;
-    for (int seq = w; seq < n_local; seq += nsw) {
-        const int seg = (int)(img - img0), par = seg & 1;
-        for (; cur_seg < seg; ++cur_seg) {
-            wait_flushed(h, cur_seg - 1);                 // queue parity of segment cur_seg - 2 is free again
-            q_push_marker(p, cur_seg & 1, kMarkEnd);
-        }
-        wait_flushed(h, seg - 1);
-        const int slot = w;   // == seq % S
+    // load-order index ls <-> granule c = ls - lead of the CTA's range (c < 0: history before the range, c >= n_local:
+    // lookahead after it; both only in ring mode, both inside the first / last image of the range)
+    long long img = (g_first - lead + w) / p.gpi;
+    int gi = (int)((g_first - lead + w) - img * p.gpi);
+    for (int ls = w; ls < n_load; ls += nsw) {
+        const int c = ls - lead;
         {
             STAT_T0();
-            mbar_wait_guarded(&h->full_bar[slot], (uint32_t)((seq / nsw) & 1), "wait for a granule");
+            mbar_wait_guarded(&h->full_bar[slot], (uint32_t)((ls / nsw) & 1), "wait for a granule");
             STAT_ACC(0);
         }
-        const int q0 = gi * p.T, npx = min(p.T, p.HW - q0);
-        const float* gran = ring + (size_t)slot * p.gran_floats;
-        const bool first = gi == 0 || seq == 0;          // first granule of the segment: its owner bootstraps the threshold
-        if (first && ld_vol(&h->thr_bits[par]) == 0u) {
-            // hints: the best channel of the better half of the pixels (16th largest of the first 32 pixel maxima; every pixel
-            // when K is large against the granule), enough to find K high peaks fast
+        if (p.ring && lane == 0) *(volatile int*)&h->landed_seq[slot] = ls + 1;
+        if (c >= 0 && c < n_local) {
+            const int seg = (int)(img - img0), par = seg & 1;
+            for (; cur_seg < seg; ++cur_seg) {
+                wait_flushed(h, cur_seg - 1);                 // queue parity of segment cur_seg - 2 is free again
+                q_push_marker(p, cur_seg & 1, kMarkEnd);
+            }
+            wait_flushed(h, seg - 1);
+            const int q0 = gi * p.T, npx = min(p.T, p.HW - q0);
+            const float* gran = ring + (size_t)slot * p.gran_floats;
+            const bool first = gi == 0 || c == 0;          // first granule of the segment: its owner bootstraps the threshold
+            const bool hinting = first && ld_vol(&h->thr_bits[par]) == 0u;
+            unsigned bits = 0u;
             float guess = ninf;
-            if (p.K * 4 <= npx) {
-                const float v = lane < npx ? pixel_max<STRIDE, HM>(gran + (size_t)lane * stride, hm) : ninf;
-                int rank = 0;
+            if (hinting) {
+                // hints: the best channel of the better half of the pixels (16th largest of the first 32 pixel maxima; every
+                // pixel when K is large against the granule), enough to find K high peaks fast
+                if (p.K * 4 <= npx) {
+                    const float v = lane < npx ? pixel_max<STRIDE, HM>(gran + (size_t)lane * stride, hm) : ninf;
+                    int rank = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) rank += __shfl_sync(kFull, v, j) > v;
-                float c = rank >= 15 ? v : ninf;
+                    for (int j = 0; j < 32; ++j) rank += __shfl_sync(kFull, v, j) > v;
+                    float cc = rank >= 15 ? v : ninf;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) c = fmaxf(c, __shfl_xor_sync(kFull, c, o));
-                guess = c;
+                    for (int o = 16; o > 0; o >>= 1) cc = fmaxf(cc, __shfl_xor_sync(kFull, cc, o));
+                    guess = cc;
+                }
+                if (lane == 0) *(volatile float*)&h->hint_guess[par] = guess;
+                bits = scan_granule<STRIDE, HM, SEG>(p, gran, npx, q0, img, guess);
+            } else {
+                int spins = 0;
+                STAT_T0();
+                while (ld_vol(&h->thr_bits[par]) == 0u) {
+                    __nanosleep(64);
+                    SPIN_GUARD(spins, "wait for the segment's threshold");
+                }
+                STAT_ACC(2);
+                STAT_LAP0();
+                bits = scan_granule<STRIDE, HM, SEG>(p, gran, npx, q0, img, __uint_as_float(ld_vol(&h->thr_bits[par])));
+                STAT_LAP(20);
             }
-            scan_granule<STRIDE, HM, SEG, 1>(p, gran, npx, q0, img, par, guess, rr);
-            q_push_marker(p, par, kMarkHintEnd);
-            int spins = 0;
-            STAT_T0();
-            while (ld_vol(&h->thr_bits[par]) == 0u) {
-                __nanosleep(64);
-                SPIN_GUARD(spins, "wait for the first threshold");
+            if (p.ring) {
+                // a record is tested against the ring: push only once the granules that hold the pixels after this one's
+                // (same image) have landed too - their owners publish that the moment they see them
+                for (int k = 1; k <= p.hg && gi + k < p.gpi; ++k) {
+                    int spins = 0;
+                    const int* word = &h->landed_seq[(slot + k) % nsw];
+                    STAT_T0();
+                    while (ld_vol(word) < ls + k + 1) {
+                        __nanosleep(40);
+                        SPIN_GUARD(spins, "wait for the lookahead granule");
+                    }
+                    STAT_ACC(16);
+                }
             }
-            STAT_ACC(1);
-            scan_granule<STRIDE, HM, SEG, 2>(p, gran, npx, q0, img, par, guess, rr);
-        } else {
-            int spins = 0;
-            STAT_T0();
-            while (ld_vol(&h->thr_bits[par]) == 0u) {
-                __nanosleep(64);
-                SPIN_GUARD(spins, "wait for the segment's threshold");
+            int n_pushed = 0;
+            if (hinting) {
+                n_pushed += push_hits(p, bits, npx, q0, par, kKindHint, true, rr);
+                q_push_marker(p, par, kMarkHintEnd);
+                int spins = 0;
+                STAT_T0();
+                while (ld_vol(&h->thr_bits[par]) == 0u) {
+                    __nanosleep(64);
+                    SPIN_GUARD(spins, "wait for the first threshold");
+                }
+                STAT_ACC(1);
+                // second pass: everything that reaches the threshold (the testers leave out the channels the hints covered)
+                bits = scan_granule<STRIDE, HM, false>(p, gran, npx, q0, img, __uint_as_float(ld_vol(&h->thr_bits[par])));
+                n_pushed += push_hits(p, bits, npx, q0, par, kKindRest, true, rr);
+            } else {
+                STAT_LAP0();
+                n_pushed += push_hits(p, bits, npx, q0, par, kKindAll, false, rr);
+                STAT_LAP(21);
+                ++rr;
             }
-            STAT_ACC(2);
-            scan_granule<STRIDE, HM, SEG, 0>(p, gran, npx, q0, img, par, 0.f, rr);
+            __syncwarp();   // every lane is done reading the granule
+            if (lane == 0) {
+                if (p.ring) {   // the granule stays until the records around it are tested (the loader warp watches the counters)
+                    *(volatile int*)&h->pushed[slot] = n_pushed;
+                    fence_cta();
+                    *(volatile int*)&h->scan_seq[slot] = ls + 1;
+                } else {
+                    mbar_arrive(&h->empty_bar[slot]);
+                }
+            }
+        } else if (lane == 0) {   // history / lookahead granule (ring mode only): resident for its neighbours' tests, not scanned
+            *(volatile int*)&h->pushed[slot] = 0;
+            fence_cta();
+            *(volatile int*)&h->scan_seq[slot] = ls + 1;
         }
-        __syncwarp();   // every lane is done reading the granule
-        if (lane == 0) mbar_arrive(&h->empty_bar[slot]);
         gi += nsw;
         while (gi >= p.gpi) {
             gi -= p.gpi;
@@ -677,54 +763,148 @@ __device__ __forceinline__ void append_peaks(const DecodeParams& p, int par, boo
     else if (rescan) scan_threshold(h, &h->thr_bits[par], shist, p.K, lane);
 }
 
-// Exact 3x3 test of one batch of records (one record per lane; lanes without one pass has = false).  Every round each
-// record tests ONE of its pending channels: nine independent global (L2) loads per lane, then a ballot and one aggregated
-// append per warp.
-template <int STRIDE, int HM>
-__device__ __forceinline__ void test_records(const DecodeParams& p, const float* img_base, int par, bool has, unsigned lo, unsigned hi) {
-    unsigned rem = has ? hi : 0u;
-    if (!__any_sync(kFull, rem != 0u)) return;
-    SharedHead* h = sm_head();
-    const int stride = STRIDE ? STRIDE : p.stride, hm = HM ? HM : p.hm, W = p.W;
-    const int q = (int)(lo & kRecPixel);
-    const int ch0 = (lo & kRecUpper) ? 32 : 0;
-    const int y = q / W, x = q - y * W;
-    const bool up = y > 0, dn = y < p.H - 1, lf = x > 0, rt = x < W - 1;
-    const int rs = W * stride;
-    const float* px = img_base + (size_t)q * stride + ch0;
+// One round of the 3x3 test: lanes with `act` test channel `ch` (relative to the record's channel base) of their record.
+// RING: the nine values come from the shared-memory ring, otherwise from global memory (L2).
+template <bool RING>
+__device__ __forceinline__ void load_window(const float* src, const int (&off)[9], const bool (&ok)[9], int ch, float& v, float& m) {
     const float ninf = __int_as_float(0xff800000);
-    do {
-        const bool act = rem != 0u;
+    float a[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        if (RING) a[k] = ok[k] ? src[off[k] + ch] : ninf;
+        else a[k] = ok[k] ? __ldcg(src + off[k] + ch) : ninf;
+    }
+    v = a[4];
+    m = fmaxf(fmaxf(fmaxf(a[0], a[1]), fmaxf(a[2], a[3])), fmaxf(fmaxf(a[5], a[6]), fmaxf(a[7], a[8])));
+}
+
+// Exact 3x3 test of one batch of records (one record per lane; lanes without one pass has = false).  A record names a
+// pixel whose best channel reached the threshold when it was scanned.  The lane reads the pixel's heatmap channels, keeps
+// the ones that (still) reach the threshold, and every round each record tests ONE of its pending channels: nine
+// independent loads per lane - from the ring (the granules around a record stay resident until it is tested:
+// shared-memory latency) or, for maps too wide for that, from global memory (L2 hits) - then a ballot and one aggregated
+// append per warp.  seg_ls0: load-order index of granule 0 of the records' image.
+template <int STRIDE, int HM>
+__device__ __forceinline__ void test_records(const DecodeParams& p, const float* img_base, int seg_ls0, int par, bool has, unsigned lo,
+                                             unsigned kind) {
+    using M = mask_t<HM>;
+    if (!__any_sync(kFull, has)) return;
+    STAT_LAP0();
+    SharedHead* h = sm_head();
+    const int stride = STRIDE ? STRIDE : p.stride, hm = HM ? HM : p.hm, W = p.W, T = p.T;
+    const int q = has ? (int)(lo & kRecPixel) : 0;
+    // row / column and (ring mode) granule / position without integer divisions (exact after one correction step)
+    int y = __float2int_rz(__fmul_rn((float)q, p.inv_W)), x = q - y * W;
+    if (x < 0) {
+        --y;
+        x += W;
+    } else if (x >= W) {
+        ++y;
+        x -= W;
+    }
+    const bool up = y > 0, dn = y < p.H - 1, lf = x > 0, rt = x < W - 1;
+    const bool ok[9] = {up && lf, up, up && rt, lf, true, rt, dn && lf, dn, dn && rt};
+    // element offsets of the nine pixels (channel 0): into the ring, or relative to the image in global memory
+    int off[9], g_own = 0;
+    if (p.ring) {
+        int g = __float2int_rz(__fmul_rn((float)q, p.inv_T)), o = q - g * T;
+        if (o < 0) {
+            --g;
+            o += T;
+        } else if (o >= T) {
+            ++g;
+            o -= T;
+        }
+        g_own = g;
+        int gr[3] = {g, g, g}, orow[3] = {o - W, o, o + W};   // granule / position of the pixels above, at and below
+        while (orow[0] < 0) {
+            orow[0] += T;
+            --gr[0];
+        }
+        while (orow[2] >= T) {
+            orow[2] -= T;
+            ++gr[2];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int base = ((seg_ls0 + gr[r]) & (kMaxSlots - 1)) * p.gran_floats;
+            off[r * 3 + 1] = base + orow[r] * stride;
+            // left / right neighbour: the same granule unless the pixel sits at its edge
+            off[r * 3 + 0] = orow[r] > 0 ? off[r * 3 + 1] - stride
+                                         : ((seg_ls0 + gr[r] - 1) & (kMaxSlots - 1)) * p.gran_floats + (T - 1) * stride;
+            off[r * 3 + 2] = orow[r] < T - 1 ? off[r * 3 + 1] + stride : ((seg_ls0 + gr[r] + 1) & (kMaxSlots - 1)) * p.gran_floats;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) off[k] = (q + (k / 3 - 1) * W + (k % 3 - 1)) * stride;
+    }
+    const float* const ring = sm_ring();
+    // the channels of the pixel to test
+    unsigned tb = ld_vol(&h->thr_bits[par]);
+    tb = tb ? tb : 1u;
+    M rem = 0;
+    if (has) {
+        const float thr_f = __uint_as_float(tb);
+        const float* own = p.ring ? ring + off[4] : img_base + off[4];
+        float vmax = __int_as_float(0xff800000);
+        M ge = 0;
+        if (HM > 0) {
+            float c[HM > 0 ? HM : 1];
+#pragma unroll
+            for (int k = 0; k < HM; ++k) c[k] = p.ring ? own[k] : __ldcg(own + k);
+#pragma unroll
+            for (int k = 0; k < HM; ++k) vmax = fmaxf(vmax, c[k]);
+            M top = 0;
+#pragma unroll
+            for (int k = 0; k < HM; ++k) {
+                ge |= (M)(c[k] >= thr_f ? 1u : 0u) << k;
+                top |= (M)(c[k] >= vmax ? 1u : 0u) << k;
+            }
+            top &= (M)0 - top;   // lowest channel holding the maximum
+            rem = kind == kKindHint ? top : ge;
+            if (kind == kKindRest && vmax >= *(volatile const float*)&h->hint_guess[par]) rem &= ~top;
+        } else {
+            M top = 0;
+            for (int k = 0; k < hm; ++k) vmax = fmaxf(vmax, p.ring ? own[k] : __ldcg(own + k));
+            for (int k = 0; k < hm; ++k) {
+                const float v = p.ring ? own[k] : __ldcg(own + k);
+                ge |= (M)(v >= thr_f ? 1u : 0u) << k;
+                top |= (M)(v >= vmax ? 1u : 0u) << k;
+            }
+            top &= (M)0 - top;
+            rem = kind == kKindHint ? top : ge;
+            if (kind == kKindRest && vmax >= *(volatile const float*)&h->hint_guess[par]) rem &= ~top;
+        }
+    }
+    STAT_LAP(17);
+    while (__any_sync(kFull, rem != 0)) {
+        const bool act = rem != 0;
         int ch = 0;
-        float v = 0.f, m = ninf;
+        float v = 0.f, m = __int_as_float(0xff800000);
         if (act) {
-            ch = __ffs((int)rem) - 1;
-            rem &= rem - 1u;
-            const float* c = px + ch;
-            v = __ldcg(c);
-            const float a0 = (up && lf) ? __ldcg(c - rs - stride) : ninf;
-            const float a1 = up ? __ldcg(c - rs) : ninf;
-            const float a2 = (up && rt) ? __ldcg(c - rs + stride) : ninf;
-            const float a3 = lf ? __ldcg(c - stride) : ninf;
-            const float a4 = rt ? __ldcg(c + stride) : ninf;
-            const float a5 = (dn && lf) ? __ldcg(c + rs - stride) : ninf;
-            const float a6 = dn ? __ldcg(c + rs) : ninf;
-            const float a7 = (dn && rt) ? __ldcg(c + rs + stride) : ninf;
-            m = fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), fmaxf(fmaxf(a4, a5), fmaxf(a6, a7)));
+            ch = sizeof(M) == 4 ? __ffs((int)rem) - 1 : __ffsll((long long)rem) - 1;
+            rem &= rem - 1;
+            if (p.ring) load_window<true>(ring, off, ok, ch, v, m);
+            else load_window<false>(img_base, off, ok, ch, v, m);
         }
         // the threshold may have moved since the scan: only scores that still reach it (and are > 0) go in
-        unsigned tb = ld_vol(&h->thr_bits[par]);
+        tb = ld_vol(&h->thr_bits[par]);
         tb = tb ? tb : 1u;
         const bool peak = act && v >= __uint_as_float(tb) && m <= v;
         const unsigned pm = __ballot_sync(kFull, peak);
+        STAT_LAP(18);
         STAT_ADD(11, 1);
         STAT_ADD(12, __popc(pm));
-        if (pm) append_peaks(p, par, peak, v, (unsigned)q * (unsigned)hm + (unsigned)(ch0 + ch), pm);
-    } while (__any_sync(kFull, rem != 0u));
+        if (pm) append_peaks(p, par, peak, v, (unsigned)q * (unsigned)hm + (unsigned)ch, pm);
+        STAT_LAP(19);
+    }
+    // ring mode: this record no longer needs its neighbourhood (the loader warp releases a granule when the records of the
+    // granules around it are all accounted for)
+    if (p.ring && has) atomicAdd(&h->tested[(seg_ls0 + g_own) & (kMaxSlots - 1)], 1);
 }
 
 template <int STRIDE, int HM>
-__device__ __forceinline__ void tester_main(const DecodeParams& p, long long img0, int n_segs) {
+__device__ __forceinline__ void tester_main(const DecodeParams& p, long long g_first, int lead, long long img0, int n_segs) {
     SharedHead* const h = sm_head();
     const int lane = threadIdx.x & 31, t = threadIdx.x >> 5;
     const int stride = STRIDE ? STRIDE : p.stride;
@@ -736,6 +916,7 @@ __device__ __forceinline__ void tester_main(const DecodeParams& p, long long img
         const int par = seg & 1;
         const unsigned long long* q = sm_queue(p, t, par);
         const float* img_base = p.yp + (size_t)(img0 + seg) * p.HW * stride;
+        const int seg_ls0 = (int)((img0 + seg) * p.gpi - g_first) + lead;   // (multiples of the slot count away when negative: see plan)
         unsigned hd = par ? head1 : head0;
         int ends = 0, spins = 0;
         while (ends < p.S) {
@@ -763,7 +944,7 @@ __device__ __forceinline__ void tester_main(const DecodeParams& p, long long img
             const bool marker = mine && (lo & kRecMarker) != 0u;
             {
                 STAT_T0();
-                test_records<STRIDE, HM>(p, img_base, par, mine && !marker, lo, hi);
+                test_records<STRIDE, HM>(p, img_base, seg_ls0, par, mine && !marker, lo, hi);
                 STAT_ACC(7);
             }
             ends += __popc(__ballot_sync(kFull, marker && (lo & 0xFFu) == kMarkEnd));
@@ -773,7 +954,7 @@ __device__ __forceinline__ void tester_main(const DecodeParams& p, long long img
                 int old = 0;
                 __syncwarp();
                 if (lane == 0) {
-                    __threadfence_block();
+                    fence_cta();
                     old = atomicAdd(&h->hint_done[par], 1);
                 }
                 old = __shfl_sync(kFull, old, 0);
@@ -785,7 +966,7 @@ __device__ __forceinline__ void tester_main(const DecodeParams& p, long long img
             }
             hd += (unsigned)n;
             __syncwarp();
-            __threadfence_block();
+            order_only();
             if (lane == 0) *(volatile unsigned*)&h->q_head[t][par] = hd;
             if (__any_sync(kFull, ld_vol(&h->compact_flag) != 0)) gather(p, false, 0);
         }
@@ -818,14 +999,20 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
     if (g0 >= g1) return;
     const long long img0 = g0 / p.gpi, imgL = (g1 - 1) / p.gpi;
     const int n_local = (int)(g1 - g0), n_segs = (int)(imgL - img0) + 1;
+    // ring mode: hg granules of history before the range and of lookahead after it (same image only) are loaded as well, so
+    // that the first / last records of the range find their neighbourhood in the ring
+    const int gi0 = (int)(g0 - img0 * p.gpi), giL = (int)(g1 - imgL * p.gpi);   // giL: first granule after the range in its image
+    const int lead = p.ring ? min(p.hg, gi0) : 0, tail = p.ring ? min(p.hg, p.gpi - giL) : 0;
+    const int n_load = lead + n_local + tail;
 
     if (tid == 0) {
         for (int k = 0; k < p.S; ++k) {
             mbar_init(&h->full_bar[k], 1);
             mbar_init(&h->empty_bar[k], 1);
+            h->landed_seq[k] = h->scan_seq[k] = h->pushed[k] = h->tested[k] = 0;
         }
         mbar_fence_init();
-        h->thr_bits[0] = h->thr_bits[1] = 0u;
+        h->thr_bits[0] = h->thr_bits[1] = p.thr0_bits;
         h->hint_done[0] = h->hint_done[1] = 0;
         h->flushed = 0;
         h->cur_par = 0;
@@ -836,26 +1023,63 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
         h->seg_done = 0;
         h->thr = 0ull;
         for (int k = 0; k < kTestWarps; ++k) h->q_tail[k][0] = h->q_tail[k][1] = h->q_head[k][0] = h->q_head[k][1] = 0u;
+#ifdef CVM_DECODE_STATS
+        for (int k = 0; k < kThreads / 32 * 24; ++k) (&h->stats[0][0])[k] = 0ull;
+        h->roles_done = 0;
+#endif
     }
     for (int k = tid; k < kScoreBins; k += kThreads) sm_shist(p)[k] = 0u;
     for (int k = tid; k < kTestWarps * 2 * kQCap; k += kThreads) sm_queue(p, 0, 0)[k] = 0ull;
     __syncthreads();   // the only CTA-wide barrier: from here on the three kinds of warps run on their own
 
     if (warp == kLoaderWarp) {
-        // ---- loader warp: granule `seq` goes to slot seq % S once its previous tenant has been scanned ----
+        // ---- loader warp: granule `ls` of the load order goes to slot ls % S once its previous tenant is free ----
         float* const ring = sm_ring();
         int slot = 0;
         long long l_img = img0;
-        int gi = (int)(g0 - img0 * p.gpi);
-        uint32_t e_parity = 0;   // parity of the empty-barrier phase that frees a slot for its next tenant
+        int gi = gi0 - lead;
+        uint32_t e_parity = 0;   // (L2 mode) parity of the empty-barrier phase that frees a slot for its next tenant
+        // ring mode: a slot is free when the records of every granule within hg of its tenant (same image) are tested.
+        // tested_upto: all granules [0, tested_upto] of the load order are scanned and their records tested;
+        // released: granules [0, released) may be overwritten; rel_end: first load-order index after `released`'s image
+        int tested_upto = -1, released = 0, rel_end = min(n_load, p.gpi - (gi0 - lead));
 #ifdef CVM_DECODE_STATS
         const long long lo_t0 = clock64();
 #endif
-        for (int seq = 0; seq < n_local; ++seq) {
-            if (seq >= p.S) {
+        for (int ls = 0; ls < n_load; ++ls) {
+            if (ls >= p.S) {
                 STAT_T0();
-                mbar_wait_guarded(&h->empty_bar[slot], e_parity, "loader waiting for a free slot");
+                if (!p.ring) {
+                    mbar_wait_guarded(&h->empty_bar[slot], e_parity, "loader waiting for a free slot");
+                } else if (lane == 0) {
+                    int spins = 0;
+                    while (released <= ls - p.S) {
+                        bool progress = false;
+                        const int c = tested_upto + 1, cs = c % p.S;
+                        if (c < n_load && ld_vol(&h->scan_seq[cs]) == c + 1) {
+                            fence_cta();
+                            if (ld_vol(&h->tested[cs]) == ld_vol(&h->pushed[cs])) {
+                                tested_upto = c;
+                                progress = true;
+                            }
+                        }
+                        if (tested_upto >= min(released + p.hg, rel_end - 1)) {
+                            if (++released == rel_end) rel_end = min(n_load, rel_end + p.gpi);
+                            progress = true;
+                        }
+                        if (!progress) {
+                            __nanosleep(40);
+                            SPIN_GUARD(spins, "loader waiting for a tested granule");
+                        }
+                    }
+                }
+                __syncwarp();
                 STAT_ACC(13);
+            }
+            if (p.ring && lane == 0) {   // counters of the slot's new tenant (nobody touches them between release and landing)
+                h->pushed[slot] = 0;
+                h->tested[slot] = 0;
+                order_only();
             }
             const int npx = min(p.T, p.HW - gi * p.T);
             const float* src = p.yp + ((size_t)l_img * p.HW + (size_t)gi * p.T) * stride;
@@ -874,7 +1098,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
             }
             if (++slot == p.S) {
                 slot = 0;
-                if (seq >= p.S) e_parity ^= 1u;
+                if (ls >= p.S) e_parity ^= 1u;
             }
             if (++gi == p.gpi) {
                 gi = 0;
@@ -883,11 +1107,16 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
         }
 #ifdef CVM_DECODE_STATS
         STAT_ADD(14, clock64() - lo_t0);
+        stats_role_done(p);
 #endif
         return;
     }
-    if (warp < kTestWarps) tester_main<STRIDE, HM>(p, img0, n_segs);
-    else if (warp - kTestWarps < p.S) scanner_main<STRIDE, HM, SEG>(p, warp - kTestWarps, g0, n_local, img0, n_segs);
+    if (warp < kTestWarps) tester_main<STRIDE, HM>(p, g0, lead, img0, n_segs);
+    else if (warp - kTestWarps < p.S) scanner_main<STRIDE, HM, SEG>(p, warp - kTestWarps, g0, n_local, lead, n_load, img0, n_segs);
+    else return;
+#ifdef CVM_DECODE_STATS
+    stats_role_done(p);
+#endif
 }
 
 struct MergeParams {
@@ -1037,30 +1266,64 @@ __global__ void __launch_bounds__(kMergeThreads) decode_merge_kernel(const Merge
 
 
 struct Plan {
-    int T, gpi, S, gran_floats, cap, compact_at, grid, max_segs, seg_keys;
+    int T, gpi, S, ring, hg, gran_floats, cap, compact_at, grid, max_segs, seg_keys;
     long long n_gran;
     size_t smem_scan, smem_merge, ws_keys, ws_total;
 };
 
 int plan_decode(const cvm_layout* L, int stride, int B, int K, int spare_sms, Plan* t) {
-    const long long HW = (long long)L->H * L->W;
-    // granule: <= 32 KB of consecutive pixels (a multiple of 32 pixels: 128-byte multiples for the bulk-copy engine)
-    int T = kGranBytes / (stride * 4) / 32 * 32;
-    if (T > kMaxT) T = kMaxT;
-    if (T < 32) T = 32;
-    if (HW < T) T = (int)((HW + 31) / 32 * 32);
+    const int W = L->W;
+    const long long HW = (long long)L->H * W;
     t->compact_at = K + kSlack;
     // a tester warp appends at most 32 keys between two looks at the compaction flag; four rounds of margin per warp
     t->cap = t->compact_at + 1 + 4 * kTestThreads;
-    const size_t fixed = smem_bytes(0, 0, t->cap, K);
-    // one ring slot per scanner warp: all kScanWarps of them when 32-pixel granules fit, fewer for very wide pixels
-    int S = kMaxSlots;
-    while (S > 2 && fixed + (size_t)S * 32 * stride * 4 + 32 > (size_t)kSmemBudget) --S;
-    for (;; T -= 32) {
-        if (T < 32) return CVM_ERR_ARG;
-        if (fixed + (size_t)S * T * stride * 4 + 32 <= (size_t)kSmemBudget) break;
+    const size_t fixed = smem_bytes(0, 0, t->cap, K) + 32;
+    if (fixed + 2 * 32 * (size_t)stride * 4 > (size_t)kSmemBudget) return CVM_ERR_ARG;
+    const size_t px_bytes = (size_t)stride * 4;
+    // Ring mode (the 3x3 neighbours of a record are read from shared memory): all kMaxSlots slots, each a whole number of
+    // image rows (then a pixel's neighbourhood lies in the granules before / after its own: hg = 1), or, for rows wider than
+    // a slot, 32-pixel multiples with hg = ceil((W + 1) / T) granules of history and lookahead (at most 3: the ring must
+    // hold hg + 1 + hg granules plus the ones in flight).
+    const long long px_slot = (long long)(((size_t)kSmemBudget - fixed) / kMaxSlots / px_bytes);
+    t->ring = 0;
+    t->hg = 0;
+    int T = 0;
+    if (HW < (1 << 24)) {
+        if (px_slot >= W) {
+            long long rows = px_slot / W;
+            if (rows > L->H) rows = L->H;
+            while (rows > 1 && rows * W * (long long)px_bytes > kGranBytes) --rows;   // keep granules <= 32 KB ...
+            while (rows > 1 && (L->H + rows - 1) / rows * (long long)B < 4LL * cvm_num_sms()) --rows;   // ... and a few per CTA
+            T = (int)(rows * W);
+            t->ring = 1;
+            t->hg = 1;
+        } else if (px_slot >= 32) {
+            const int T2 = (int)(px_slot / 32 * 32);
+            const int hg = (W + 1 + T2 - 1) / T2;
+            if (hg <= 3) {
+                T = T2;
+                t->ring = 1;
+                t->hg = hg;
+            }
+        }
     }
-    t->S = S;
+    if (t->ring) {
+        t->S = kMaxSlots;
+    } else {
+        // L2 mode: granules of <= 32 KB (a multiple of 32 pixels), one ring slot per scanner warp: all kScanWarps of them
+        // when 32-pixel granules fit, fewer for very wide pixels
+        T = (int)(kGranBytes / px_bytes / 32 * 32);
+        if (T > kMaxT) T = kMaxT;
+        if (T < 32) T = 32;
+        if (HW < T) T = (int)((HW + 31) / 32 * 32);
+        int S = kMaxSlots;
+        while (S > 2 && fixed + (size_t)S * 32 * px_bytes > (size_t)kSmemBudget) --S;
+        for (;; T -= 32) {
+            if (T < 32) return CVM_ERR_ARG;
+            if (fixed + (size_t)S * T * px_bytes <= (size_t)kSmemBudget) break;
+        }
+        t->S = S;
+    }
     t->T = T;
     t->gran_floats = T * stride;
     t->gpi = (int)((HW + T - 1) / T);
@@ -1149,13 +1412,23 @@ int decode_impl(const cvm_layout* L, const float* y_pred, int pred_stride, int B
     p.keys = static_cast<unsigned long long*>(ws);
     p.counts = reinterpret_cast<int*>(static_cast<unsigned char*>(ws) + t.ws_keys);
     p.rescan_step = K / 2 > 8 ? K / 2 : 8;
+#ifdef CVM_EXPERIMENT
+    if (const char* e = getenv("CVM_DECODE_THR0")) {   // experiment only (results are wrong): start every segment at this score
+        const float f = (float)atof(e);
+        memcpy(&p.thr0_bits, &f, 4);
+    }
+#endif
+    p.ring = t.ring;
+    p.hg = t.hg;
+    p.inv_T = 1.0f / (float)t.T;
+    p.inv_W = 1.0f / (float)L->W;
     p.seg_out = seg_out;
     p.seg_off = seg_off;
     p.seg_n = seg_n;
 
     // the bulk-copy engine needs 16-byte granules: base pointer aligned and every image a whole number of them (full
     // granules are T*stride*4 bytes with T % 32 == 0, the partial last granule of an image then ends on one too)
-    const bool bulk = cvm_aligned16(y_pred) && (((long long)p.HW * pred_stride) % 4 == 0);
+    const bool bulk = cvm_aligned16(y_pred) && (((long long)p.HW * pred_stride) % 4 == 0) && (((long long)t.T * pred_stride) % 4 == 0);
     if (pred_stride == 14 && L->hm == 10) rc = launch_scan<14, 10>(p, t, bulk, st);        // CenterNet, 10 classes
     else if (pred_stride == 16 && L->hm == 10) rc = launch_scan<16, 10>(p, t, bulk, st);   // CenterTracker
     else if (pred_stride == 20 && L->hm == 10) rc = launch_scan<20, 10>(p, t, bulk, st);   // multitask head

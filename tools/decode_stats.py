@@ -23,6 +23,6 @@ v = list(out)
 n_cta = 148
 names = ["scanner: wait full barrier", "scanner: wait first threshold (hint owner)", "scanner: wait segment threshold", "scanner: wait flush",
          "scanner: queue back-pressure (lane cycles)", "scanner: total", "tester: idle", "tester: test_records", "tester: total", "records",
-         "batches", "test rounds", "peaks appended", "loader: wait free slot", "loader: total", "tester: gather at segment end"]
+         "batches", "test rounds", "peaks appended", "loader: wait free slot", "loader: total", "tester: gather at segment end", "scanner: wait lookahead granule", "tester: test preamble", "tester: window loads + vote", "tester: append", "scanner: scan (steady)", "scanner: push (steady)"]
 for n, x in zip(names, v):
     print(f"{n:48s} {x:16d}  per CTA {x / n_cta:14.1f}")
