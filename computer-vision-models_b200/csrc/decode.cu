@@ -44,6 +44,7 @@ constexpr int kLoaderWarp = kTestWarps + kScanWarps;
 constexpr int kThreads = (kLoaderWarp + 1) * 32;
 constexpr int kMergeThreads = 256;
 constexpr int kMaxSlots = kScanWarps;   // ring depth (granules): one slot per active scanner warp
+constexpr int kCtr = 2 * kMaxSlots;
 constexpr int kMaxT = 1024;        // pixels per granule (a scanner lane keeps one hit bit per pixel of its granule: 32 x 32)
 constexpr int kGranBytes = 32768;  // target granule size
 constexpr int kUnroll = 4;         // pixels per scanner lane and iteration
@@ -112,9 +113,11 @@ struct SharedHead {
     unsigned long long thr;       // K-th key of the last exact select
     // ring mode, per slot (sequence numbers are 1 + the index of the granule in this CTA's load order, so 0 = never)
     int landed_seq[kMaxSlots];    // the slot's tenant has arrived (set by the owning scanner warp)
-    int scan_seq[kMaxSlots];      // ... and has been scanned: `pushed` is final
-    int pushed[kMaxSlots];        // records pushed for the tenant
-    int tested[kMaxSlots];        // records of the tenant the testers are done with
+    // per granule, indexed by its load-order index & (kCtr - 1): twice the ring depth, because the records of a granule may
+    // still be pending when its slot has already been handed to the granule kMaxSlots later
+    int scan_seq[kCtr];           // the granule has been scanned: `pushed` is final
+    int pushed[kCtr];             // records pushed for the granule
+    int tested[kCtr];             // records of the granule the testers are done with
 #ifdef CVM_DECODE_STATS
     unsigned long long stats[kThreads / 32][24];   // private to each warp's lane 0: plain adds
     int roles_done;
@@ -510,6 +513,17 @@ __device__ __forceinline__ void q_push_marker(const DecodeParams& p, int par, un
     __syncwarp();
 }
 
+// Ring mode: has granule `ls` of the load order landed in its slot?  Its owner publishes that in landed_seq the moment it sees
+// it; before that, anybody may ask the slot's full barrier - but only once the slot's previous tenant (ls - kMaxSlots) is
+// known to have landed, because the parity test cannot tell phases two apart.
+__device__ __forceinline__ bool granule_landed(SharedHead* h, int ls) {
+    const int s = ls & (kMaxSlots - 1);
+    const int seq = ld_vol(&h->landed_seq[s]);
+    if (seq >= ls + 1) return true;
+    if (seq >= ls + 1 - kMaxSlots) return mbar_try_wait(&h->full_bar[s], (uint32_t)((ls / kMaxSlots) & 1));
+    return false;
+}
+
 // ---- scanner warps ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void wait_flushed(SharedHead* h, int want) {
     if (want <= 0) return;
@@ -596,6 +610,115 @@ __device__ __forceinline__ int push_hits(const DecodeParams& p, unsigned bits, i
     return n_pushed;
 }
 
+// Ring mode.  For every hit bit (see scan_granule) of the granule in `slot`: pick the pixel's channels (kKindAll: those
+// that reach the threshold; kKindHint: its best one; kKindRest: like kKindAll without the one a hint covered) and test each
+// against the five neighbours that are already in the ring - the row above and the pixel's left / right neighbours (the
+// granules before this one are still resident, see the loader).  What survives is pushed to the testers as (pixel, channel,
+// score) and only waits for the row below.  Lanes walk their own hit pixels; every round each lane tests one (pixel,
+// channel) pair and the warp pushes the survivors with one reservation.  Returns the records pushed.
+template <int STRIDE, int HM>
+__device__ __forceinline__ int prefilter_push(const DecodeParams& p, int slot, int npx, int q0, unsigned bits, int par, unsigned kind,
+                                              float guess, bool spread, unsigned& rr) {
+    using M = mask_t<HM>;
+    SharedHead* h = sm_head();
+    const float* const ring = sm_ring();
+    const int lane = threadIdx.x & 31;
+    const int stride = STRIDE ? STRIDE : p.stride, hm = HM ? HM : p.hm, W = p.W, T = p.T, G = p.gran_floats;
+    const float ninf = __int_as_float(0xff800000);
+    int n_pushed = 0;
+    M chans = 0;                       // channels of the lane's current pixel that are still to test
+    int q = 0, own = 0, o_ul = 0, o_um = 0, o_ur = 0, o_l = 0, o_r = 0;
+    bool up = false, lf = false, rt = false, rt_here = false;
+    float thr_f = 0.f;
+    while (__any_sync(kFull, chans != 0 || bits != 0u)) {
+        if (chans == 0 && bits != 0u) {
+            const int j = __ffs((int)bits) - 1;
+            bits &= bits - 1u;
+            const int pix = (j / kUnroll) * (32 * kUnroll) + (j % kUnroll) * 32 + lane;
+            q = q0 + pix;
+            int y = __float2int_rz(__fmul_rn((float)q, p.inv_W)), x = q - y * W;   // exact after one correction step
+            if (x < 0) {
+                --y;
+                x += W;
+            } else if (x >= W) {
+                ++y;
+                x -= W;
+            }
+            up = y > 0;
+            lf = x > 0;
+            rt = x < W - 1;
+            rt_here = rt && pix < T - 1;   // (the right neighbour of a granule's last pixel is in the NEXT granule: the tester's)
+            own = slot * G + pix * stride;
+            o_l = pix > 0 ? own - stride : ((slot - 1) & (kMaxSlots - 1)) * G + (T - 1) * stride;
+            o_r = own + stride;
+            int o_up = pix - W, s_up = slot;
+            while (o_up < 0) {
+                o_up += T;
+                s_up = (s_up - 1) & (kMaxSlots - 1);
+            }
+            o_um = s_up * G + o_up * stride;
+            o_ul = o_up > 0 ? o_um - stride : ((s_up - 1) & (kMaxSlots - 1)) * G + (T - 1) * stride;
+            o_ur = o_up < T - 1 ? o_um + stride : ((s_up + 1) & (kMaxSlots - 1)) * G;
+            unsigned tb = ld_vol(&h->thr_bits[par]);
+            tb = tb ? tb : 1u;
+            thr_f = __uint_as_float(tb);
+            const float* px = ring + own;
+            float vmax = ninf;
+            M ge = 0, top = 0;
+            if (HM > 0) {
+                float c[HM > 0 ? HM : 1];
+#pragma unroll
+                for (int k = 0; k < HM; ++k) c[k] = px[k];
+#pragma unroll
+                for (int k = 0; k < HM; ++k) vmax = fmaxf(vmax, c[k]);
+#pragma unroll
+                for (int k = 0; k < HM; ++k) {
+                    ge |= (M)(c[k] >= thr_f ? 1u : 0u) << k;
+                    top |= (M)(c[k] >= vmax ? 1u : 0u) << k;
+                }
+            } else {
+                for (int k = 0; k < hm; ++k) vmax = fmaxf(vmax, px[k]);
+                for (int k = 0; k < hm; ++k) {
+                    ge |= (M)(px[k] >= thr_f ? 1u : 0u) << k;
+                    top |= (M)(px[k] >= vmax ? 1u : 0u) << k;
+                }
+            }
+            top &= (M)0 - top;   // lowest channel holding the maximum
+            chans = kind == kKindHint ? top : ge;
+            if (kind == kKindRest && vmax >= guess) chans &= ~top;
+        }
+        bool cand = false;
+        int ch = 0;
+        float v = 0.f;
+        if (chans != 0) {
+            ch = sizeof(M) == 4 ? __ffs((int)chans) - 1 : __ffsll((long long)chans) - 1;
+            chans &= chans - 1;
+            v = ring[own + ch];
+            const float a0 = (up && lf) ? ring[o_ul + ch] : ninf, a1 = up ? ring[o_um + ch] : ninf;
+            const float a2 = (up && rt) ? ring[o_ur + ch] : ninf;
+            const float a3 = lf ? ring[o_l + ch] : ninf, a4 = rt_here ? ring[o_r + ch] : ninf;
+            const float m5 = fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), a4);
+            cand = v >= thr_f && m5 <= v;
+        }
+        const unsigned bal = __ballot_sync(kFull, cand);
+        if (bal) {
+            const int n = __popc(bal);
+            const int t = (int)(rr % kTestWarps);
+            if (spread) ++rr;
+            unsigned pos = 0;
+            if (lane == 0) {
+                pos = atomicAdd(&h->q_tail[t][par], (unsigned)n);
+                q_wait_space(h, t, par, pos + (unsigned)n);
+            }
+            pos = __shfl_sync(kFull, pos, 0);
+            order_only();
+            if (cand) q_store(sm_queue(p, t, par), pos + __popc(bal & ((1u << lane) - 1u)), (unsigned)q | ((unsigned)ch << 24), __float_as_uint(v));
+            n_pushed += n;
+        }
+    }
+    return n_pushed;
+}
+
 template <int STRIDE, int HM, bool SEG>
 __device__ __forceinline__ void scanner_main(const DecodeParams& p, int w, long long g_first, int n_local, int lead, int n_load,
                                              long long img0, int n_segs) {
@@ -663,14 +786,14 @@ __device__ __forceinline__ void scanner_main(const DecodeParams& p, int w, long 
                 STAT_LAP(20);
             }
             if (p.ring) {
-                // a record is tested against the ring: push only once the granules that hold the pixels after this one's
-                // (same image) have landed too - their owners publish that the moment they see them
+                // a record waits for the row below only in the testers' hands: push (and, before that, run the tests against
+                // the rows above) only once the granules that hold the pixels after this one's (same image) have landed too.
+                // Nothing here waits for a tester, and the testers never wait for a granule: no cycle.
                 for (int k = 1; k <= p.hg && gi + k < p.gpi; ++k) {
                     int spins = 0;
-                    const int* word = &h->landed_seq[(slot + k) % nsw];
                     STAT_T0();
-                    while (ld_vol(word) < ls + k + 1) {
-                        __nanosleep(40);
+                    while (!__all_sync(kFull, granule_landed(h, ls + k))) {
+                        __nanosleep(32);
                         SPIN_GUARD(spins, "wait for the lookahead granule");
                     }
                     STAT_ACC(16);
@@ -678,7 +801,8 @@ __device__ __forceinline__ void scanner_main(const DecodeParams& p, int w, long 
             }
             int n_pushed = 0;
             if (hinting) {
-                n_pushed += push_hits(p, bits, npx, q0, par, kKindHint, true, rr);
+                n_pushed += p.ring ? prefilter_push<STRIDE, HM>(p, slot, npx, q0, bits, par, kKindHint, guess, true, rr)
+                                   : push_hits(p, bits, npx, q0, par, kKindHint, true, rr);
                 q_push_marker(p, par, kMarkHintEnd);
                 int spins = 0;
                 STAT_T0();
@@ -689,27 +813,29 @@ __device__ __forceinline__ void scanner_main(const DecodeParams& p, int w, long 
                 STAT_ACC(1);
                 // second pass: everything that reaches the threshold (the testers leave out the channels the hints covered)
                 bits = scan_granule<STRIDE, HM, false>(p, gran, npx, q0, img, __uint_as_float(ld_vol(&h->thr_bits[par])));
-                n_pushed += push_hits(p, bits, npx, q0, par, kKindRest, true, rr);
+                n_pushed += p.ring ? prefilter_push<STRIDE, HM>(p, slot, npx, q0, bits, par, kKindRest, guess, true, rr)
+                                   : push_hits(p, bits, npx, q0, par, kKindRest, true, rr);
             } else {
                 STAT_LAP0();
-                n_pushed += push_hits(p, bits, npx, q0, par, kKindAll, false, rr);
+                n_pushed += p.ring ? prefilter_push<STRIDE, HM>(p, slot, npx, q0, bits, par, kKindAll, guess, false, rr)
+                                   : push_hits(p, bits, npx, q0, par, kKindAll, false, rr);
                 STAT_LAP(21);
                 ++rr;
             }
             __syncwarp();   // every lane is done reading the granule
             if (lane == 0) {
-                if (p.ring) {   // the granule stays until the records around it are tested (the loader warp watches the counters)
-                    *(volatile int*)&h->pushed[slot] = n_pushed;
+                if (p.ring) {   // the granule stays while the scans / records around it need it (the loader warp watches the counters)
+                    *(volatile int*)&h->pushed[ls & (kCtr - 1)] = n_pushed;
                     fence_cta();
-                    *(volatile int*)&h->scan_seq[slot] = ls + 1;
+                    *(volatile int*)&h->scan_seq[ls & (kCtr - 1)] = ls + 1;
                 } else {
                     mbar_arrive(&h->empty_bar[slot]);
                 }
             }
         } else if (lane == 0) {   // history / lookahead granule (ring mode only): resident for its neighbours' tests, not scanned
-            *(volatile int*)&h->pushed[slot] = 0;
+            *(volatile int*)&h->pushed[ls & (kCtr - 1)] = 0;
             fence_cta();
-            *(volatile int*)&h->scan_seq[slot] = ls + 1;
+            *(volatile int*)&h->scan_seq[ls & (kCtr - 1)] = ls + 1;
         }
         gi += nsw;
         while (gi >= p.gpi) {
@@ -900,7 +1026,69 @@ __device__ __forceinline__ void test_records(const DecodeParams& p, const float*
     }
     // ring mode: this record no longer needs its neighbourhood (the loader warp releases a granule when the records of the
     // granules around it are all accounted for)
-    if (p.ring && has) atomicAdd(&h->tested[(seg_ls0 + g_own) & (kMaxSlots - 1)], 1);
+    if (p.ring && has) atomicAdd(&h->tested[(seg_ls0 + g_own) & (kCtr - 1)], 1);
+}
+
+// Ring mode: a record is a (pixel, channel, score) that already beat the row above and its left / right neighbours
+// (prefilter_push).  What is left is the row below (and the right neighbour when that sits in the next granule): wait until
+// the granules that hold them have landed (their owners publish that the moment they see them), three or four shared loads,
+// a ballot and one aggregated append per warp.
+template <int STRIDE, int HM>
+__device__ __forceinline__ void confirm_records(const DecodeParams& p, int seg_ls0, int par, bool has, unsigned lo, unsigned hi) {
+    if (!__any_sync(kFull, has)) return;
+    STAT_LAP0();
+    SharedHead* h = sm_head();
+    const float* const ring = sm_ring();
+    const int stride = STRIDE ? STRIDE : p.stride, hm = HM ? HM : p.hm, W = p.W, T = p.T, G = p.gran_floats;
+    const float ninf = __int_as_float(0xff800000);
+    const int q = has ? (int)(lo & 0xFFFFFFu) : 0, ch = (int)((lo >> 24) & 63u);
+    const float v = __uint_as_float(hi);
+    int y = __float2int_rz(__fmul_rn((float)q, p.inv_W)), x = q - y * W;   // exact after one correction step
+    if (x < 0) {
+        --y;
+        x += W;
+    } else if (x >= W) {
+        ++y;
+        x -= W;
+    }
+    int g = __float2int_rz(__fmul_rn((float)q, p.inv_T)), o = q - g * T;
+    if (o < 0) {
+        --g;
+        o += T;
+    } else if (o >= T) {
+        ++g;
+        o -= T;
+    }
+    const bool dn = has && y < p.H - 1, lf = x > 0, rt = x < W - 1;
+    const bool right_later = has && rt && o == T - 1;    // the right neighbour sits in the next granule
+    int o_dn = o + W, g_dn = g;
+    while (o_dn >= T) {
+        o_dn -= T;
+        ++g_dn;
+    }
+    // (the scanner pushed this record only after the granules of the row below had landed: nothing to wait for)
+    STAT_LAP(17);
+    float m = ninf;
+    if (dn) {
+        const int o_dm = ((seg_ls0 + g_dn) & (kMaxSlots - 1)) * G + o_dn * stride + ch;
+        const int o_dl = o_dn > 0 ? o_dm - stride : ((seg_ls0 + g_dn - 1) & (kMaxSlots - 1)) * G + (T - 1) * stride + ch;
+        const int o_dr = o_dn < T - 1 ? o_dm + stride : ((seg_ls0 + g_dn + 1) & (kMaxSlots - 1)) * G + ch;
+        const float a0 = lf ? ring[o_dl] : ninf, a1 = ring[o_dm], a2 = rt ? ring[o_dr] : ninf;
+        m = fmaxf(a0, fmaxf(a1, a2));
+    }
+    if (right_later) m = fmaxf(m, ring[((seg_ls0 + g + 1) & (kMaxSlots - 1)) * G + ch]);
+    // the threshold may have moved since the scan: only scores that still reach it (and are > 0) go in
+    unsigned tb = ld_vol(&h->thr_bits[par]);
+    tb = tb ? tb : 1u;
+    const bool peak = has && v >= __uint_as_float(tb) && m <= v;
+    const unsigned pm = __ballot_sync(kFull, peak);
+    STAT_LAP(18);
+    STAT_ADD(11, 1);
+    STAT_ADD(12, __popc(pm));
+    if (pm) append_peaks(p, par, peak, v, (unsigned)q * (unsigned)hm + (unsigned)ch, pm);
+    STAT_LAP(19);
+    // this record no longer needs the ring (the loader warp releases a granule when the scans and records that read it are done)
+    if (has) atomicAdd(&h->tested[(seg_ls0 + g) & (kCtr - 1)], 1);
 }
 
 template <int STRIDE, int HM>
@@ -944,7 +1132,8 @@ __device__ __forceinline__ void tester_main(const DecodeParams& p, long long g_f
             const bool marker = mine && (lo & kRecMarker) != 0u;
             {
                 STAT_T0();
-                test_records<STRIDE, HM>(p, img_base, seg_ls0, par, mine && !marker, lo, hi);
+                if (p.ring) confirm_records<STRIDE, HM>(p, seg_ls0, par, mine && !marker, lo, hi);
+                else test_records<STRIDE, HM>(p, img_base, seg_ls0, par, mine && !marker, lo, hi);
                 STAT_ACC(7);
             }
             ends += __popc(__ballot_sync(kFull, marker && (lo & 0xFFu) == kMarkEnd));
@@ -1009,8 +1198,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
         for (int k = 0; k < p.S; ++k) {
             mbar_init(&h->full_bar[k], 1);
             mbar_init(&h->empty_bar[k], 1);
-            h->landed_seq[k] = h->scan_seq[k] = h->pushed[k] = h->tested[k] = 0;
+            h->landed_seq[k] = 0;
         }
+        for (int k = 0; k < kCtr; ++k) h->scan_seq[k] = h->pushed[k] = h->tested[k] = 0;
         mbar_fence_init();
         h->thr_bits[0] = h->thr_bits[1] = p.thr0_bits;
         h->hint_done[0] = h->hint_done[1] = 0;
@@ -1042,7 +1232,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
         // ring mode: a slot is free when the records of every granule within hg of its tenant (same image) are tested.
         // tested_upto: all granules [0, tested_upto] of the load order are scanned and their records tested;
         // released: granules [0, released) may be overwritten; rel_end: first load-order index after `released`'s image
-        int tested_upto = -1, released = 0, rel_end = min(n_load, p.gpi - (gi0 - lead));
+        int scan_upto = -1, tested_upto = -1, released = 0, rel_end = min(n_load, p.gpi - (gi0 - lead));
 #ifdef CVM_DECODE_STATS
         const long long lo_t0 = clock64();
 #endif
@@ -1055,20 +1245,25 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
                     int spins = 0;
                     while (released <= ls - p.S) {
                         bool progress = false;
-                        const int c = tested_upto + 1, cs = c % p.S;
+                        const int c = scan_upto + 1, cs = c & (kCtr - 1);
                         if (c < n_load && ld_vol(&h->scan_seq[cs]) == c + 1) {
-                            fence_cta();
-                            if (ld_vol(&h->tested[cs]) == ld_vol(&h->pushed[cs])) {
-                                tested_upto = c;
-                                progress = true;
-                            }
+                            scan_upto = c;
+                            progress = true;
                         }
-                        if (tested_upto >= min(released + p.hg, rel_end - 1)) {
+                        const int d = tested_upto + 1, ds = d & (kCtr - 1);
+                        if (d <= scan_upto && ld_vol(&h->tested[ds]) == ld_vol(&h->pushed[ds])) {
+                            tested_upto = d;
+                            progress = true;
+                        }
+                        // granule `released` is read by the scans of the next hg granules of its image (their rows above)
+                        // and by the records of the granules before it (their row below)
+                        // (tested_upto >= released - 1 also keeps the counter entries, reused every kCtr granules, apart)
+                        if (scan_upto >= min(released + p.hg, rel_end - 1) && tested_upto >= released - 1) {
                             if (++released == rel_end) rel_end = min(n_load, rel_end + p.gpi);
                             progress = true;
                         }
                         if (!progress) {
-                            __nanosleep(40);
+                            __nanosleep(20);
                             SPIN_GUARD(spins, "loader waiting for a tested granule");
                         }
                     }
@@ -1076,9 +1271,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
                 __syncwarp();
                 STAT_ACC(13);
             }
-            if (p.ring && lane == 0) {   // counters of the slot's new tenant (nobody touches them between release and landing)
-                h->pushed[slot] = 0;
-                h->tested[slot] = 0;
+            if (p.ring && lane == 0) {   // counters of the new granule (the entry's previous user, kCtr granules ago, is long done)
+                h->pushed[ls & (kCtr - 1)] = 0;
+                h->tested[ls & (kCtr - 1)] = 0;
                 order_only();
             }
             const int npx = min(p.T, p.HW - gi * p.T);
