@@ -83,6 +83,7 @@ struct DecodeParams {
     int seg_keys;                 // keys a segment can publish (>= K)
     unsigned long long* keys;     // [grid][max_segs][seg_keys]
     int* counts;                  // [grid][max_segs]
+    uint2* meta;                  // [grid][max_segs]: x = score bits every published key reaches, y = 1 if that bound is verified
     int rescan_step;              // appends after which the score histogram is scanned again
     unsigned int thr0_bits;       // threshold a segment starts with (0: none, bootstrap with hints)
     int ring;                     // 1: the 3x3 neighbours of a record are read from the ring (granules stay resident until the
@@ -102,6 +103,10 @@ struct SharedHead {
     int misc[4];
     unsigned int thr_bits[2];     // per segment parity: running threshold score (float bits); 0 = not established (hint phase)
     float hint_guess[2];          // pixels whose maximum reaches this were hinted (first granule of the segment)
+    unsigned int thr_init[2];     // what the segment started with: 0 = hints (exact bootstrap), else a PROVISIONAL threshold
+                                  // predicted from the previous segment (see flush_segment)
+    unsigned int next_thr;        // flush_segment: prediction for the next segment
+    int target[2];                // peaks the running threshold keeps at or above it (K, or 2K behind a provisional threshold)
     int hint_done[2];             // tester warps that have seen the end of the segment's hints
     int flushed;                  // segments published so far
     int cur_par;                  // parity of the segment the testers are working on
@@ -360,9 +365,33 @@ __device__ __noinline__ void compact_buffer(const DecodeParams& p) {
     group_sync(nt);
 }
 
+// Lower edge (float bits) of the highest score bin with at least `target` buffered candidates at or above it; 0 if there
+// are fewer.  One warp, nobody appending.
+__device__ __forceinline__ unsigned hist_edge(const unsigned int* shist, int top, int target, int lane) {
+    unsigned above = 0;
+    for (int base = top; base >= 0; base -= 32) {
+        const int bin = base - lane;
+        unsigned incl = bin >= 0 ? shist[bin] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const unsigned hit = __ballot_sync(kFull, above + incl >= (unsigned)target);
+        if (hit) return (unsigned)(base - (__ffs(hit) - 1)) << kScoreShift;
+        above += __shfl_sync(kFull, incl, 31);
+    }
+    return 0u;
+}
+
 // End of a (CTA, image) segment: publish the candidates that still reach the running threshold (the merge kernel does
-// the exact select; only a segment with more than kSegKeys of them selects its best K first), reset the selection
-// state, open the next segment but one for the scanners.  All tester threads, every record of the segment consumed.
+// the exact select; only a segment with more than kSegKeys of them selects its best K first) together with that bound
+// and whether it is VERIFIED - at least K peaks of this segment reach it, or the segment was bootstrapped exactly -
+// or still the provisional value the segment started with (then the merge kernel checks it against the whole image).
+// Then reset the selection state and hand the next segment its provisional threshold: the score that about 2K peaks of
+// THIS segment reach (images of a batch look alike: the next image then yields about 2K records instead of the several
+// thousand a bootstrap from nothing costs; if the prediction is too high for it, the merge kernel notices and recomputes
+// that image the slow way).  All tester threads, every record of the segment consumed.
 __device__ __noinline__ void flush_segment(const DecodeParams& p, int seg) {
     const int tid = threadIdx.x, nt = kTestThreads;
     SharedHead* h = sm_head();
@@ -374,6 +403,22 @@ __device__ __noinline__ void flush_segment(const DecodeParams& p, int seg) {
     int n = h->count;
     unsigned thr_bits = h->thr_bits[par];
     if (thr_bits == 0u) thr_bits = 1u;
+    const unsigned init = h->thr_init[par];
+    // init 0: exact bootstrap from hints; 1: "every positive score"; anything else is provisional until a histogram scan or
+    // an exact select (both need >= K peaks at or above the new value) has raised the running threshold beyond it
+    bool verified = init <= 1u || thr_bits != init;
+    // prediction for the next segment (warp 0; the histogram holds every peak appended in this segment)
+    if (tid < 32) {
+        int want = 2 * p.K;
+        if (want > p.compact_at - 64) want = p.compact_at - 64;
+        unsigned next = n >= want ? hist_edge(shist, h->maxbin, want, tid) : 0u;
+        if (next == 0u) {   // fewer than that many peaks seen: go a little below what this segment ended with
+            const float f = __uint_as_float(thr_bits) * (n >= p.K ? 0.9f : 0.7f);
+            next = __float_as_uint(f);
+        }
+        if (next < 1u || thr_bits <= 1u) next = 1u;   // (a segment that never got past "every positive score" predicts nothing)
+        if (tid == 0) h->next_thr = next;
+    }
     int above = 0;
     for (int i = tid; i < n; i += nt) above += (unsigned)(cand[i] >> 32) >= thr_bits;
     above = group_sum(above, nt, &h->misc[0]);
@@ -381,6 +426,8 @@ __device__ __noinline__ void flush_segment(const DecodeParams& p, int seg) {
         select_topk(cand, n, p.K, h->hist, sm_keep(p), h->misc, &h->thr, nt);
         n = p.K;
         for (int i = tid; i < n; i += nt) out[i] = cand[i];
+        thr_bits = (unsigned)(h->thr >> 32);   // every published key reaches the K-th one
+        verified = true;
     } else {
         if (tid == 0) h->misc[1] = 0;
         group_sync(nt);
@@ -394,17 +441,22 @@ __device__ __noinline__ void flush_segment(const DecodeParams& p, int seg) {
     group_sync(nt);
     if (tid == 0) {
         p.counts[o] = n;
+        p.meta[o] = make_uint2(thr_bits, verified ? 1u : 0u);
+        const unsigned next = p.thr0_bits ? p.thr0_bits : h->next_thr;
         h->count = 0;
         h->thr = 0ull;
-        h->thr_bits[par] = p.thr0_bits;   // the parity is reused by segment seg + 2: back to the hint phase
+        h->thr_bits[par] = 0u;
         h->hint_done[par] = 0;
+        h->thr_bits[par ^ 1] = next;          // the next segment starts here (its scanners wait for this flush) ...
+        h->thr_init[par ^ 1] = next;          // ... and this is what it has to get past to verify it
+        h->target[par ^ 1] = next > 1u ? min(2 * p.K, p.compact_at - 64) : p.K;
         h->cur_par = par ^ 1;
         h->scanned = 0;
         h->maxbin = 0;
         h->compact_flag = 0;
         h->seg_done = 0;
         fence_cta();
-        *(volatile int*)&h->flushed = seg + 1;   // scanners waiting to enter segment seg + 2 go on
+        *(volatile int*)&h->flushed = seg + 1;
     }
     group_sync(nt);
 }
@@ -751,7 +803,7 @@ __device__ __forceinline__ void scanner_main(const DecodeParams& p, int w, long 
                 wait_flushed(h, cur_seg - 1);                 // queue parity of segment cur_seg - 2 is free again
                 q_push_marker(p, cur_seg & 1, kMarkEnd);
             }
-            wait_flushed(h, seg - 1);
+            wait_flushed(h, seg);    // the flush of the previous segment hands this one its provisional threshold
             const int q0 = gi * p.T, npx = min(p.T, p.HW - q0);
             const float* gran = ring + (size_t)slot * p.gran_floats;
             const bool first = gi == 0 || c == 0;          // first granule of the segment: its owner bootstraps the threshold
@@ -867,7 +919,7 @@ __device__ __forceinline__ void append_peaks(const DecodeParams& p, int par, boo
     if (lane == 0) {
         base = (unsigned)atomicAdd(&h->count, (int)total);
         const int cnt = (int)(base + total);
-        rescan = cnt >= p.K && cnt - ld_vol(&h->scanned) >= p.rescan_step;
+        rescan = cnt >= ld_vol(&h->target[par]) && cnt - ld_vol(&h->scanned) >= p.rescan_step;
         if (cnt > p.cap) {   // cannot happen: every warp stops within one round of the mark (see plan_decode)
             printf("decode_scan_kernel: candidate buffer overflow (cta %d)\n", (int)blockIdx.x);
             __trap();
@@ -886,7 +938,7 @@ __device__ __forceinline__ void append_peaks(const DecodeParams& p, int par, boo
     }
     __syncwarp();
     if (__any_sync(kFull, ld_vol(&h->compact_flag) != 0)) gather(p, false, 0);
-    else if (rescan) scan_threshold(h, &h->thr_bits[par], shist, p.K, lane);
+    else if (rescan) scan_threshold(h, &h->thr_bits[par], shist, ld_vol(&h->target[par]), lane);
 }
 
 // One round of the 3x3 test: lanes with `act` test channel `ch` (relative to the record's channel base) of their record.
@@ -1203,6 +1255,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
         for (int k = 0; k < kCtr; ++k) h->scan_seq[k] = h->pushed[k] = h->tested[k] = 0;
         mbar_fence_init();
         h->thr_bits[0] = h->thr_bits[1] = p.thr0_bits;
+        h->thr_init[0] = h->thr_init[1] = 0u;
+        h->target[0] = h->target[1] = p.K;
         h->hint_done[0] = h->hint_done[1] = 0;
         h->flushed = 0;
         h->cur_par = 0;
@@ -1325,6 +1379,7 @@ struct MergeParams {
     const cvm_roi* rois;
     const unsigned long long* keys;
     const int* counts;
+    const uint2* meta;
     float* scores;
     int32_t* cls;
     long long* flat;
@@ -1343,13 +1398,25 @@ __global__ void __launch_bounds__(kMergeThreads) decode_merge_kernel(const Merge
     unsigned long long* const keep = all + kMergeCap + K;                              // [K]
     unsigned long long* const sorted = keep + K;                                       // [K]
 
-    // the scan CTAs whose step range [g*n/G, (g+1)*n/G) overlaps this image's steps [lo, hi)
+    // the scan CTAs whose granule range [g*n/G, (g+1)*n/G) overlaps this image's granules [lo, hi)
     const long long n_ch = p.n_steps, G = p.grid;
     const long long lo = (long long)b * p.spi, hi = lo + p.spi;
-    long long g = lo * G / n_ch;
-    while (g + 1 < G && (g + 1) * n_ch / G <= lo) ++g;
-    int n = 0;
-    for (; g < G; ++g) {
+    long long g_first = lo * G / n_ch;
+    while (g_first + 1 < G && (g_first + 1) * n_ch / G <= lo) ++g_first;
+    // Segments that ran behind a PROVISIONAL threshold (predicted from the image before, see flush_segment) published
+    // every peak at or above it; the prediction holds for this image iff at least K of all its published peaks reach the
+    // largest provisional threshold among its segments (then the K-th best score does, and nothing below a threshold can
+    // belong to the top K).
+    unsigned need_bits = 0u;
+    for (long long g = g_first; g < G; ++g) {
+        const long long s0 = g * n_ch / G, s1 = (g + 1) * n_ch / G;
+        if (s0 >= hi) break;
+        if (s1 <= s0) continue;
+        const uint2 mt = p.meta[(size_t)g * p.max_segs + (int)(b - s0 / p.spi)];
+        if (!mt.y && mt.x > need_bits) need_bits = mt.x;
+    }
+    int n = 0, n_ok = 0;
+    for (long long g = g_first; g < G; ++g) {
         const long long s0 = g * n_ch / G, s1 = (g + 1) * n_ch / G;
         if (s0 >= hi) break;
         if (s1 <= s0) continue;
@@ -1362,8 +1429,65 @@ __global__ void __launch_bounds__(kMergeThreads) decode_merge_kernel(const Merge
             n = K;
         }
         const unsigned long long* src = p.keys + o * p.seg_keys;
-        for (int i = tid; i < cnt; i += kMergeThreads) all[n + i] = src[i];
+        for (int i = tid; i < cnt; i += kMergeThreads) {
+            const unsigned long long k = src[i];
+            all[n + i] = k;
+            n_ok += (unsigned)(k >> 32) >= need_bits;
+        }
         n += cnt;
+    }
+    if (need_bits != 0u) {
+        if (tid == 0) s_misc[0] = 0;
+        group_sync(kMergeThreads);
+        n_ok = __reduce_add_sync(kFull, n_ok);
+        if ((tid & 31) == 0 && n_ok) atomicAdd(&s_misc[0], n_ok);
+        group_sync(kMergeThreads);
+        n_ok = s_misc[0];
+        group_sync(kMergeThreads);
+        if (n_ok < K) {
+            // The prediction was too high for this image: exact top-K of the whole image by this CTA alone (rare).  One
+            // pixel per thread and step, channel by channel; a positive value above the running K-th key is tested against
+            // its 3x3 neighbourhood in global memory; the buffer is cut back to its best K when it fills up.
+            n = 0;
+            if (tid == 0) {
+                s_misc[3] = 0;
+                s_thr = 0ull;
+            }
+            group_sync(kMergeThreads);
+            const int HW = p.H * p.W;
+            const float* img = p.yp + (size_t)b * HW * p.stride;
+            const float ninf = __int_as_float(0xff800000);
+            for (int pix0 = 0; pix0 < HW; pix0 += kMergeThreads) {
+                const int pix = pix0 + tid;
+                const int y = pix / p.W, x = pix - y * p.W;
+                for (int c = 0; c < p.hm; ++c) {
+                    if (pix < HW) {
+                        const float* q = img + (size_t)pix * p.stride + c;
+                        const float v = *q;
+                        const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) |
+                                                       (unsigned long long)(0xFFFFFFFFu - ((unsigned)pix * (unsigned)p.hm + (unsigned)c));
+                        if (v > 0.f && key > *(volatile unsigned long long*)&s_thr) {
+                            float m = ninf;
+                            for (int dy = -1; dy <= 1; ++dy)
+                                for (int dx = -1; dx <= 1; ++dx) {
+                                    if ((dy | dx) == 0 || y + dy < 0 || y + dy >= p.H || x + dx < 0 || x + dx >= p.W) continue;
+                                    m = fmaxf(m, q[(dy * p.W + dx) * p.stride]);
+                                }
+                            if (m <= v) all[atomicAdd(&s_misc[3], 1)] = key;
+                        }
+                    }
+                    group_sync(kMergeThreads);
+                    const int cnt = *(volatile int*)&s_misc[3];
+                    group_sync(kMergeThreads);
+                    if (cnt > kMergeCap - kMergeThreads) {   // (room for one more step of appends is kept)
+                        select_topk(all, cnt, K, hist, keep, s_misc, &s_thr, kMergeThreads);   // leaves s_thr = K-th key
+                        if (tid == 0) s_misc[3] = K;
+                        group_sync(kMergeThreads);
+                    }
+                }
+            }
+            n = *(volatile int*)&s_misc[3];
+        }
     }
     group_sync(kMergeThreads);
     if (n > K) {
@@ -1535,7 +1659,7 @@ int plan_decode(const cvm_layout* L, int stride, int B, int K, int spare_sms, Pl
     t->smem_merge = ((size_t)kMergeCap + 3 * (size_t)K) * 8;
     t->seg_keys = K > kSegKeys ? K : kSegKeys;
     t->ws_keys = (size_t)grid * t->max_segs * t->seg_keys * 8;
-    t->ws_total = t->ws_keys + (size_t)grid * t->max_segs * 4;
+    t->ws_total = t->ws_keys + (size_t)grid * t->max_segs * 4 + (size_t)grid * t->max_segs * 8 + 16;
     return CVM_OK;
 }
 
@@ -1606,6 +1730,7 @@ int decode_impl(const cvm_layout* L, const float* y_pred, int pred_stride, int B
     p.seg_keys = t.seg_keys;
     p.keys = static_cast<unsigned long long*>(ws);
     p.counts = reinterpret_cast<int*>(static_cast<unsigned char*>(ws) + t.ws_keys);
+    p.meta = reinterpret_cast<uint2*>(static_cast<unsigned char*>(ws) + ((t.ws_keys + (size_t)t.grid * t.max_segs * 4 + 7) & ~(size_t)7));
     p.rescan_step = K / 2 > 8 ? K / 2 : 8;
 #ifdef CVM_EXPERIMENT
     if (const char* e = getenv("CVM_DECODE_THR0")) {   // experiment only (results are wrong): start every segment at this score
@@ -1652,6 +1777,7 @@ int decode_impl(const cvm_layout* L, const float* y_pred, int pred_stride, int B
     m.rois = rois;
     m.keys = p.keys;
     m.counts = p.counts;
+    m.meta = p.meta;
     m.scores = scores;
     m.cls = cls;
     m.flat = flat;
