@@ -84,6 +84,9 @@ struct DecodeParams {
     unsigned long long* keys;     // [grid][max_segs][seg_keys]
     int* counts;                  // [grid][max_segs]
     uint2* meta;                  // [grid][max_segs]: x = score bits every published key reaches, y = 1 if that bound is verified
+    unsigned long long* hint;     // [2] in the workspace: {cookie, predicted threshold bits} left by the previous call (a cache:
+                                  // any content is safe, a wrong prediction only costs the slow path of the merge kernel)
+    unsigned long long cookie;
     int rescan_step;              // appends after which the score histogram is scanned again
     unsigned int thr0_bits;       // threshold a segment starts with (0: none, bootstrap with hints)
     int ring;                     // 1: the 3x3 neighbours of a record are read from the ring (granules stay resident until the
@@ -389,9 +392,10 @@ __device__ __forceinline__ unsigned hist_edge(const unsigned int* shist, int top
 // and whether it is VERIFIED - at least K peaks of this segment reach it, or the segment was bootstrapped exactly -
 // or still the provisional value the segment started with (then the merge kernel checks it against the whole image).
 // Then reset the selection state and hand the next segment its provisional threshold: the score that about 2K peaks of
-// THIS segment reach (images of a batch look alike: the next image then yields about 2K records instead of the several
-// thousand a bootstrap from nothing costs; if the prediction is too high for it, the merge kernel notices and recomputes
-// that image the slow way).  All tester threads, every record of the segment consumed.
+// THIS segment reach (images of a batch look alike: an image then yields about 2K records instead of the several thousand
+// a bootstrap from nothing costs; if the prediction is too high for it, the merge kernel notices and recomputes that
+// image the slow way).  The prediction serves the next segment BUT ONE of this CTA (the next one is already being
+// scanned) and, from CTA 0, the next call.  All tester threads, every record of the segment consumed.
 __device__ __noinline__ void flush_segment(const DecodeParams& p, int seg) {
     const int tid = threadIdx.x, nt = kTestThreads;
     SharedHead* h = sm_head();
@@ -445,11 +449,16 @@ __device__ __noinline__ void flush_segment(const DecodeParams& p, int seg) {
         const unsigned next = p.thr0_bits ? p.thr0_bits : h->next_thr;
         h->count = 0;
         h->thr = 0ull;
-        h->thr_bits[par] = 0u;
         h->hint_done[par] = 0;
-        h->thr_bits[par ^ 1] = next;          // the next segment starts here (its scanners wait for this flush) ...
-        h->thr_init[par ^ 1] = next;          // ... and this is what it has to get past to verify it
-        h->target[par ^ 1] = next > 1u ? min(2 * p.K, p.compact_at - 64) : p.K;
+        // the next segment (other parity) is already under way with the prediction of the segment before this one; this
+        // parity's next tenant, segment seg + 2, starts here ...
+        h->thr_bits[par] = next;
+        h->thr_init[par] = next;              // ... and this is what it has to get past to verify it
+        h->target[par] = next > 1u ? min(2 * p.K, p.compact_at - 64) : p.K;
+        if (blockIdx.x == 0) {                // the prediction the next call starts with
+            p.hint[1] = next;
+            p.hint[0] = p.cookie;
+        }
         h->cur_par = par ^ 1;
         h->scanned = 0;
         h->maxbin = 0;
@@ -803,7 +812,7 @@ __device__ __forceinline__ void scanner_main(const DecodeParams& p, int w, long 
                 wait_flushed(h, cur_seg - 1);                 // queue parity of segment cur_seg - 2 is free again
                 q_push_marker(p, cur_seg & 1, kMarkEnd);
             }
-            wait_flushed(h, seg);    // the flush of the previous segment hands this one its provisional threshold
+            wait_flushed(h, seg - 1);    // (the flush of segment seg - 2 frees this parity and leaves its provisional threshold)
             const int q0 = gi * p.T, npx = min(p.T, p.HW - q0);
             const float* gran = ring + (size_t)slot * p.gran_floats;
             const bool first = gi == 0 || c == 0;          // first granule of the segment: its owner bootstraps the threshold
@@ -1254,9 +1263,13 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
         }
         for (int k = 0; k < kCtr; ++k) h->scan_seq[k] = h->pushed[k] = h->tested[k] = 0;
         mbar_fence_init();
-        h->thr_bits[0] = h->thr_bits[1] = p.thr0_bits;
-        h->thr_init[0] = h->thr_init[1] = 0u;
-        h->target[0] = h->target[1] = p.K;
+        // a prediction left in the workspace by the previous call on (presumably) similar data; none: bootstrap from hints
+        unsigned start = p.thr0_bits;
+        if (!start && p.hint[0] == p.cookie) start = (unsigned)p.hint[1];
+        if (start >= 0x7f800000u) start = 0u;   // (not a positive finite score)
+        h->thr_bits[0] = h->thr_bits[1] = start;
+        h->thr_init[0] = h->thr_init[1] = start;
+        h->target[0] = h->target[1] = start > 1u ? min(2 * p.K, p.compact_at - 64) : p.K;
         h->hint_done[0] = h->hint_done[1] = 0;
         h->flushed = 0;
         h->cur_par = 0;
@@ -1659,7 +1672,7 @@ int plan_decode(const cvm_layout* L, int stride, int B, int K, int spare_sms, Pl
     t->smem_merge = ((size_t)kMergeCap + 3 * (size_t)K) * 8;
     t->seg_keys = K > kSegKeys ? K : kSegKeys;
     t->ws_keys = (size_t)grid * t->max_segs * t->seg_keys * 8;
-    t->ws_total = t->ws_keys + (size_t)grid * t->max_segs * 4 + (size_t)grid * t->max_segs * 8 + 16;
+    t->ws_total = t->ws_keys + (size_t)grid * t->max_segs * 4 + (size_t)grid * t->max_segs * 8 + 16 + 16;
     return CVM_OK;
 }
 
@@ -1731,6 +1744,10 @@ int decode_impl(const cvm_layout* L, const float* y_pred, int pred_stride, int B
     p.keys = static_cast<unsigned long long*>(ws);
     p.counts = reinterpret_cast<int*>(static_cast<unsigned char*>(ws) + t.ws_keys);
     p.meta = reinterpret_cast<uint2*>(static_cast<unsigned char*>(ws) + ((t.ws_keys + (size_t)t.grid * t.max_segs * 4 + 7) & ~(size_t)7));
+    p.hint = reinterpret_cast<unsigned long long*>(p.meta + (size_t)t.grid * t.max_segs);
+    // the prediction is only taken from a call with the same map geometry and K
+    p.cookie = 0x63766d6864656331ull ^ ((unsigned long long)L->H << 48) ^ ((unsigned long long)L->W << 32) ^
+               ((unsigned long long)L->hm << 24) ^ ((unsigned long long)pred_stride << 12) ^ (unsigned long long)K;
     p.rescan_step = K / 2 > 8 ? K / 2 : 8;
 #ifdef CVM_EXPERIMENT
     if (const char* e = getenv("CVM_DECODE_THR0")) {   // experiment only (results are wrong): start every segment at this score
