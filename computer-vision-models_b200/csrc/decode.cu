@@ -47,7 +47,10 @@ constexpr int kMaxSlots = kScanWarps;   // ring depth (granules): one slot per a
 constexpr int kCtr = 2 * kMaxSlots;
 constexpr int kMaxT = 1024;        // pixels per granule (a scanner lane keeps one hit bit per pixel of its granule: 32 x 32)
 constexpr int kGranBytes = 32768;  // target granule size
-constexpr int kUnroll = 4;         // pixels per scanner lane and iteration
+#ifndef CVM_UNROLL
+#define CVM_UNROLL 4
+#endif
+constexpr int kUnroll = CVM_UNROLL;   // pixels per scanner lane and iteration
 constexpr int kQShift = 7;
 constexpr int kQCap = 1 << kQShift;   // records per queue (one queue per tester warp and segment parity)
 constexpr int kSlack = 1536;       // buffer entries beyond K before the (rare) fallback compaction
@@ -66,6 +69,15 @@ constexpr unsigned kKindHint = 2u;     // hint: test the pixel's best channel on
 constexpr unsigned kKindRest = 3u;     // second pass over a hinted granule: like kKindAll without the channel a hint covered
 constexpr unsigned kMarkEnd = 1u, kMarkHintEnd = 2u;
 
+// what a scan CTA leaves per (CTA, image) segment next to its keys
+struct SegMeta {
+    int count;                    // keys published
+    unsigned int thr_bits;        // score bits every published key reaches
+    unsigned int verified;        // 1: at least K peaks of the segment reach thr_bits, or the segment was bootstrapped exactly;
+                                  // 0: thr_bits is still the provisional threshold the segment started with
+    unsigned int pad;
+};
+
 struct DecodeParams {
     const float* yp;
     int stride, H, W, hm, K;
@@ -82,8 +94,7 @@ struct DecodeParams {
     int max_segs;                 // images one CTA range can touch
     int seg_keys;                 // keys a segment can publish (>= K)
     unsigned long long* keys;     // [grid][max_segs][seg_keys]
-    int* counts;                  // [grid][max_segs]
-    uint2* meta;                  // [grid][max_segs]: x = score bits every published key reaches, y = 1 if that bound is verified
+    SegMeta* segmeta;             // [grid][max_segs]
     unsigned long long* hint;     // [2] in the workspace: {cookie, predicted threshold bits} left by the previous call (a cache:
                                   // any content is safe, a wrong prediction only costs the slow path of the merge kernel)
     unsigned long long cookie;
@@ -109,6 +120,7 @@ struct SharedHead {
     unsigned int thr_init[2];     // what the segment started with: 0 = hints (exact bootstrap), else a PROVISIONAL threshold
                                   // predicted from the previous segment (see flush_segment)
     unsigned int next_thr;        // flush_segment: prediction for the next segment
+    unsigned int pub_thr;         // flush_segment: score bound of the published keys
     int target[2];                // peaks the running threshold keeps at or above it (K, or 2K behind a provisional threshold)
     int hint_done[2];             // tester warps that have seen the end of the segment's hints
     int flushed;                  // segments published so far
@@ -196,6 +208,12 @@ __device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity
 // -DCVM_DECODE_STATS: per-warp cycle / event counters for tuning (tools/decode_stats.py); never in the shipped build
 #ifdef CVM_DECODE_STATS
 __device__ unsigned long long g_decode_stats[32];
+__device__ unsigned long long g_decode_cta[4][256];   // per CTA: globaltimer at start, loader done, scanners done, testers done
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 #define STAT_T0() const long long st_t0_ = clock64()
 #define STAT_LAP(i) do { const long long t_ = clock64(); if ((threadIdx.x & 31) == 0) sm_head()->stats[threadIdx.x >> 5][i] += (unsigned long long)(t_ - st_lap_); st_lap_ = t_; } while (0)
 #define STAT_LAP0() long long st_lap_ = clock64()
@@ -413,7 +431,10 @@ __device__ __noinline__ void flush_segment(const DecodeParams& p, int seg) {
     bool verified = init <= 1u || thr_bits != init;
     // prediction for the next segment (warp 0; the histogram holds every peak appended in this segment)
     if (tid < 32) {
-        int want = 2 * p.K;
+#ifndef CVM_PRED_MULT
+#define CVM_PRED_MULT 3          /* in halves of K: the prediction is the score that 1.5 K peaks of the segment reach */
+#endif
+        int want = CVM_PRED_MULT * p.K / 2;
         if (want > p.compact_at - 64) want = p.compact_at - 64;
         unsigned next = n >= want ? hist_edge(shist, h->maxbin, want, tid) : 0u;
         if (next == 0u) {   // fewer than that many peaks seen: go a little below what this segment ended with
@@ -421,7 +442,18 @@ __device__ __noinline__ void flush_segment(const DecodeParams& p, int seg) {
             next = __float_as_uint(f);
         }
         if (next < 1u || thr_bits <= 1u) next = 1u;   // (a segment that never got past "every positive score" predicts nothing)
-        if (tid == 0) h->next_thr = next;
+        // what is worth publishing: with K peaks or more in the buffer, only the score bins that hold the best K of them
+        // (a verified bound: K peaks of this segment reach it) - the merge kernel ranks what it is given
+        const unsigned pub = n >= p.K ? hist_edge(shist, h->maxbin, p.K, tid) : 0u;
+        if (tid == 0) {
+            h->next_thr = next;
+            h->pub_thr = pub;
+        }
+    }
+    group_sync(nt);
+    if (h->pub_thr > thr_bits) {
+        thr_bits = h->pub_thr;
+        verified = true;
     }
     int above = 0;
     for (int i = tid; i < n; i += nt) above += (unsigned)(cand[i] >> 32) >= thr_bits;
@@ -444,8 +476,7 @@ __device__ __noinline__ void flush_segment(const DecodeParams& p, int seg) {
     for (int i = tid; i < kScoreBins; i += nt) shist[i] = 0u;
     group_sync(nt);
     if (tid == 0) {
-        p.counts[o] = n;
-        p.meta[o] = make_uint2(thr_bits, verified ? 1u : 0u);
+        p.segmeta[o] = SegMeta{n, thr_bits, verified ? 1u : 0u, 0u};
         const unsigned next = p.thr0_bits ? p.thr0_bits : h->next_thr;
         h->count = 0;
         h->thr = 0ull;
@@ -454,7 +485,7 @@ __device__ __noinline__ void flush_segment(const DecodeParams& p, int seg) {
         // parity's next tenant, segment seg + 2, starts here ...
         h->thr_bits[par] = next;
         h->thr_init[par] = next;              // ... and this is what it has to get past to verify it
-        h->target[par] = next > 1u ? min(2 * p.K, p.compact_at - 64) : p.K;
+        h->target[par] = next > 1u ? min(CVM_PRED_MULT * p.K / 2, p.compact_at - 64) : p.K;
         if (blockIdx.x == 0) {                // the prediction the next call starts with
             p.hint[1] = next;
             p.hint[0] = p.cookie;
@@ -1269,7 +1300,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
         if (start >= 0x7f800000u) start = 0u;   // (not a positive finite score)
         h->thr_bits[0] = h->thr_bits[1] = start;
         h->thr_init[0] = h->thr_init[1] = start;
-        h->target[0] = h->target[1] = start > 1u ? min(2 * p.K, p.compact_at - 64) : p.K;
+        h->target[0] = h->target[1] = start > 1u ? min(CVM_PRED_MULT * p.K / 2, p.compact_at - 64) : p.K;
         h->hint_done[0] = h->hint_done[1] = 0;
         h->flushed = 0;
         h->cur_par = 0;
@@ -1288,6 +1319,12 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
     for (int k = tid; k < kScoreBins; k += kThreads) sm_shist(p)[k] = 0u;
     for (int k = tid; k < kTestWarps * 2 * kQCap; k += kThreads) sm_queue(p, 0, 0)[k] = 0ull;
     __syncthreads();   // the only CTA-wide barrier: from here on the three kinds of warps run on their own
+#ifdef CVM_DECODE_STATS
+    if (tid == 0) {
+        g_decode_cta[0][blockIdx.x] = gtime();
+        g_decode_cta[2][blockIdx.x] = g_decode_cta[3][blockIdx.x] = 0ull;
+    }
+#endif
 
     if (warp == kLoaderWarp) {
         // ---- loader warp: granule `ls` of the load order goes to slot ls % S once its previous tenant is free ----
@@ -1369,6 +1406,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
         }
 #ifdef CVM_DECODE_STATS
         STAT_ADD(14, clock64() - lo_t0);
+        if (lane == 0) g_decode_cta[1][blockIdx.x] = gtime();
         stats_role_done(p);
 #endif
         return;
@@ -1377,9 +1415,14 @@ __global__ void __launch_bounds__(kThreads, 1) decode_scan_kernel(const __grid_c
     else if (warp - kTestWarps < p.S) scanner_main<STRIDE, HM, SEG>(p, warp - kTestWarps, g0, n_local, lead, n_load, img0, n_segs);
     else return;
 #ifdef CVM_DECODE_STATS
+    if (lane == 0) atomicMax(&g_decode_cta[warp < kTestWarps ? 3 : 2][blockIdx.x], gtime());
     stats_role_done(p);
 #endif
 }
+
+// images whose predicted threshold did not hold and that the merge kernel recomputed the slow way (monitoring: a steady
+// stream of these means the batches are too unlike each other for the prediction to pay)
+__device__ unsigned long long g_decode_fallbacks;
 
 struct MergeParams {
     const float* yp;
@@ -1391,8 +1434,7 @@ struct MergeParams {
     float R;
     const cvm_roi* rois;
     const unsigned long long* keys;
-    const int* counts;
-    const uint2* meta;
+    const SegMeta* segmeta;
     float* scores;
     int32_t* cls;
     long long* flat;
@@ -1405,49 +1447,82 @@ __global__ void __launch_bounds__(kMergeThreads) decode_merge_kernel(const Merge
     __shared__ unsigned int hist[256];
     __shared__ int s_misc[4];
     __shared__ unsigned long long s_thr;
+    __shared__ int s_cnt[kMergeThreads], s_off[kMergeThreads], s_g[2];
+    __shared__ unsigned int s_need;
+    __shared__ int s_total;
 
     const int tid = threadIdx.x, b = blockIdx.x, K = p.K;
     unsigned long long* const all = reinterpret_cast<unsigned long long*>(g_smem);   // [kMergeCap + K]
     unsigned long long* const keep = all + kMergeCap + K;                              // [K]
     unsigned long long* const sorted = keep + K;                                       // [K]
 
-    // the scan CTAs whose granule range [g*n/G, (g+1)*n/G) overlaps this image's granules [lo, hi)
+    // the scan CTAs whose granule range [g*n/G, (g+1)*n/G) overlaps this image's granules [lo, hi) (every CTA has at least
+    // one granule: the grid never exceeds their number)
     const long long n_ch = p.n_steps, G = p.grid;
-    const long long lo = (long long)b * p.spi, hi = lo + p.spi;
-    long long g_first = lo * G / n_ch;
-    while (g_first + 1 < G && (g_first + 1) * n_ch / G <= lo) ++g_first;
+    if (tid == 0) {   // (64-bit divisions: once per CTA)
+        const long long lo = (long long)b * p.spi, hi = lo + p.spi;
+        long long gf = lo * G / n_ch;
+        while (gf + 1 < G && (gf + 1) * n_ch / G <= lo) ++gf;
+        long long gl = gf;
+        while (gl + 1 < G && (gl + 1) * n_ch / G < hi) ++gl;
+        s_g[0] = (int)gf;
+        s_g[1] = (int)gl;
+        s_need = 0u;
+        s_total = 0;
+    }
+    group_sync(kMergeThreads);
+    const long long g_first = s_g[0], g_last = s_g[1];
+    const int n_over = (int)(g_last - g_first + 1);
     // Segments that ran behind a PROVISIONAL threshold (predicted from the image before, see flush_segment) published
     // every peak at or above it; the prediction holds for this image iff at least K of all its published peaks reach the
     // largest provisional threshold among its segments (then the K-th best score does, and nothing below a threshold can
-    // belong to the top K).
-    unsigned need_bits = 0u;
-    for (long long g = g_first; g < G; ++g) {
-        const long long s0 = g * n_ch / G, s1 = (g + 1) * n_ch / G;
-        if (s0 >= hi) break;
-        if (s1 <= s0) continue;
-        const uint2 mt = p.meta[(size_t)g * p.max_segs + (int)(b - s0 / p.spi)];
-        if (!mt.y && mt.x > need_bits) need_bits = mt.x;
+    // belong to the top K).  One thread per segment fetches its record (one round trip for all of them).
+    for (int t = tid; t < n_over; t += kMergeThreads) {
+        const long long g = g_first + t;
+        const SegMeta mt = p.segmeta[(size_t)g * p.max_segs + (int)(b - (g * n_ch / G) / p.spi)];
+        if (t < kMergeThreads) {
+            s_cnt[t] = mt.count;
+            s_off[t] = (int)((size_t)g * p.max_segs + (int)(b - (g * n_ch / G) / p.spi));
+        }
+        if (!mt.verified) atomicMax(&s_need, mt.thr_bits);
+        atomicAdd(&s_total, mt.count);
     }
+    group_sync(kMergeThreads);
+    const unsigned need_bits = s_need;
     int n = 0, n_ok = 0;
-    for (long long g = g_first; g < G; ++g) {
-        const long long s0 = g * n_ch / G, s1 = (g + 1) * n_ch / G;
-        if (s0 >= hi) break;
-        if (s1 <= s0) continue;
-        const int seg = (int)(b - s0 / p.spi);
-        const size_t o = (size_t)g * p.max_segs + seg;
-        const int cnt = p.counts[o];
-        if (n + cnt > kMergeCap) {   // cnt <= seg_keys <= kMergeCap / 4, so n > K here
-            group_sync(kMergeThreads);
-            select_topk(all, n, K, hist, keep, s_misc, &s_thr, kMergeThreads);
-            n = K;
+    if (n_over <= 32 && s_total <= kMergeCap) {
+        // the usual case: a few segments, everything fits: all keys in one sweep
+        int base = 0;
+        for (int t = 0; t < n_over; ++t) {
+            const size_t o = (size_t)s_off[t];
+            const int cnt = s_cnt[t];
+            const unsigned long long* src = p.keys + o * p.seg_keys;
+            for (int i = tid; i < cnt; i += kMergeThreads) {
+                const unsigned long long k = src[i];
+                all[base + i] = k;
+                n_ok += (unsigned)(k >> 32) >= need_bits;
+            }
+            base += cnt;
         }
-        const unsigned long long* src = p.keys + o * p.seg_keys;
-        for (int i = tid; i < cnt; i += kMergeThreads) {
-            const unsigned long long k = src[i];
-            all[n + i] = k;
-            n_ok += (unsigned)(k >> 32) >= need_bits;
+        n = base;
+    } else {
+        for (long long g = g_first; g <= g_last; ++g) {
+            const int seg = (int)(b - (g * n_ch / G) / p.spi);
+            const size_t o = (size_t)g * p.max_segs + seg;
+            const int cnt = p.segmeta[o].count;
+            if (n + cnt > kMergeCap) {   // cnt <= seg_keys <= kMergeCap / 4, so n > K here
+                group_sync(kMergeThreads);
+                select_topk(all, n, K, hist, keep, s_misc, &s_thr, kMergeThreads);
+                n = K;
+            }
+            const unsigned long long* src = p.keys + o * p.seg_keys;
+            for (int i = tid; i < cnt; i += kMergeThreads) {
+                const unsigned long long k = src[i];
+                all[n + i] = k;
+                n_ok += (unsigned)(k >> 32) >= need_bits;
+            }
+            n += cnt;
         }
-        n += cnt;
     }
     if (need_bits != 0u) {
         if (tid == 0) s_misc[0] = 0;
@@ -1465,6 +1540,7 @@ __global__ void __launch_bounds__(kMergeThreads) decode_merge_kernel(const Merge
             if (tid == 0) {
                 s_misc[3] = 0;
                 s_thr = 0ull;
+                atomicAdd(&g_decode_fallbacks, 1ull);
             }
             group_sync(kMergeThreads);
             const int HW = p.H * p.W;
@@ -1503,17 +1579,19 @@ __global__ void __launch_bounds__(kMergeThreads) decode_merge_kernel(const Merge
         }
     }
     group_sync(kMergeThreads);
-    if (n > K) {
+    if (n > 1024) {   // many keys: radix select first
         select_topk(all, n, K, hist, keep, s_misc, &s_thr, kMergeThreads);
         n = K;
     }
-    // rank sort (keys are distinct): descending
+    // rank by counting (keys are distinct): the K best in descending order; no barriers (the segments publish little more
+    // than their best K keys, so n is a few hundred at most here)
     for (int i = tid; i < n; i += kMergeThreads) {
         const unsigned long long k = all[i];
         int rank = 0;
         for (int j = 0; j < n; ++j) rank += all[j] > k;
-        sorted[rank] = k;
+        if (rank < K) sorted[rank] = k;
     }
+    if (n > K) n = K;
     group_sync(kMergeThreads);
 
     const int hm = p.hm, W = p.W;
@@ -1672,7 +1750,7 @@ int plan_decode(const cvm_layout* L, int stride, int B, int K, int spare_sms, Pl
     t->smem_merge = ((size_t)kMergeCap + 3 * (size_t)K) * 8;
     t->seg_keys = K > kSegKeys ? K : kSegKeys;
     t->ws_keys = (size_t)grid * t->max_segs * t->seg_keys * 8;
-    t->ws_total = t->ws_keys + (size_t)grid * t->max_segs * 4 + (size_t)grid * t->max_segs * 8 + 16 + 16;
+    t->ws_total = t->ws_keys + (size_t)grid * t->max_segs * sizeof(SegMeta) + 16;
     return CVM_OK;
 }
 
@@ -1742,9 +1820,8 @@ int decode_impl(const cvm_layout* L, const float* y_pred, int pred_stride, int B
     p.max_segs = t.max_segs;
     p.seg_keys = t.seg_keys;
     p.keys = static_cast<unsigned long long*>(ws);
-    p.counts = reinterpret_cast<int*>(static_cast<unsigned char*>(ws) + t.ws_keys);
-    p.meta = reinterpret_cast<uint2*>(static_cast<unsigned char*>(ws) + ((t.ws_keys + (size_t)t.grid * t.max_segs * 4 + 7) & ~(size_t)7));
-    p.hint = reinterpret_cast<unsigned long long*>(p.meta + (size_t)t.grid * t.max_segs);
+    p.segmeta = reinterpret_cast<SegMeta*>(static_cast<unsigned char*>(ws) + t.ws_keys);
+    p.hint = reinterpret_cast<unsigned long long*>(p.segmeta + (size_t)t.grid * t.max_segs);
     // the prediction is only taken from a call with the same map geometry and K
     p.cookie = 0x63766d6864656331ull ^ ((unsigned long long)L->H << 48) ^ ((unsigned long long)L->W << 32) ^
                ((unsigned long long)L->hm << 24) ^ ((unsigned long long)pred_stride << 12) ^ (unsigned long long)K;
@@ -1793,8 +1870,7 @@ int decode_impl(const cvm_layout* L, const float* y_pred, int pred_stride, int B
     m.R = (float)L->R;
     m.rois = rois;
     m.keys = p.keys;
-    m.counts = p.counts;
-    m.meta = p.meta;
+    m.segmeta = p.segmeta;
     m.scores = scores;
     m.cls = cls;
     m.flat = flat;
@@ -1807,6 +1883,8 @@ int decode_impl(const cvm_layout* L, const float* y_pred, int pred_stride, int B
         CVM_CHECK_CUDA(cudaFuncSetAttribute(decode_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_merge));
         merge_configured = true;
     }
+    // (tried: programmatic dependent launch of the merge kernel, griddepcontrol.launch_dependents at the top of the scan:
+    // 0.143 ms instead of 0.139 for the pair - the early-resident merge CTAs are in the way more than the launch gap costs)
     decode_merge_kernel<<<B, kMergeThreads, t.smem_merge, st>>>(m);
     CVM_CHECK_LAUNCH("decode_merge_kernel");
     return CVM_OK;
@@ -1827,6 +1905,12 @@ extern "C" int cvm_decode_topk(const cvm_layout* L, const float* y_pred, int pre
     return decode_impl(L, y_pred, pred_stride, B, K, rois, scores, cls, flat, centers, boxes, track, 0, 0, nullptr, ws, ws_bytes, stream);
 }
 
+extern "C" long long cvm_decode_fallback_count(void) {
+    unsigned long long v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_decode_fallbacks, sizeof(v)) != cudaSuccess) return -1;
+    return (long long)v;
+}
+
 extern "C" int cvm_decode_topk_semseg(const cvm_layout* L, const float* y_pred, int pred_stride, int B, int K,
                                       const cvm_roi* rois, float* scores, int32_t* cls, long long* flat, float* centers,
                                       float* boxes, float* track, int seg_off, int seg_n, unsigned char* seg_ids, void* ws,
@@ -1837,6 +1921,11 @@ extern "C" int cvm_decode_topk_semseg(const cvm_layout* L, const float* y_pred, 
 }
 
 #ifdef CVM_DECODE_STATS
+extern "C" int cvm_decode_cta_times(unsigned long long* out /* [4][256] */) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_decode_cta, sizeof(unsigned long long) * 4 * 256);
+    return 0;
+}
 extern "C" int cvm_decode_stats(unsigned long long* out32, int reset) {
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(out32, g_decode_stats, sizeof(unsigned long long) * 32);

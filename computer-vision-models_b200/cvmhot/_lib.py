@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcvmhot.so")
+# CVMHOT_LIB: load another build of the same library (tools/ build variants with -DCVM_EXPERIMENT / -DCVM_DECODE_STATS)
+LIB_PATH = os.environ.get("CVMHOT_LIB") or os.path.join(_HERE, "lib", "libcvmhot.so")
 
 CVM_MAX_FIELDS = 8
 CVM_NPART = 16
@@ -74,6 +75,8 @@ def lib():
     L.cvm_decode_topk.argtypes = [LP, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.cvm_decode_topk_semseg.restype = i32
     L.cvm_decode_topk_semseg.argtypes = [LP, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, sz, vp]
+    L.cvm_decode_fallback_count.restype = i64
+    L.cvm_decode_fallback_count.argtypes = []
     L.cvm_decode_window9_workspace_bytes.restype = sz
     L.cvm_decode_window9_workspace_bytes.argtypes = [LP, i32]
     L.cvm_decode_window9.restype = i32
@@ -88,7 +91,7 @@ def lib():
 
 EXPORTS = [
     "cvm_last_error", "cvm_version", "cvm_prepare_objects", "cvm_render_gt", "cvm_render_prev_hm", "cvm_fill_heatmap_inplace", "cvm_loss_workspace_bytes",
-    "cvm_loss_fwd", "cvm_loss_finalize", "cvm_loss_bwd", "cvm_decode_topk_workspace_bytes", "cvm_decode_topk", "cvm_decode_topk_semseg",
+    "cvm_loss_fwd", "cvm_loss_finalize", "cvm_loss_bwd", "cvm_decode_topk_workspace_bytes", "cvm_decode_topk", "cvm_decode_topk_semseg", "cvm_decode_fallback_count",
     "cvm_decode_window9_workspace_bytes", "cvm_decode_window9", "cvm_semseg_argmax", "cvm_track_associate",
 ]
 

@@ -163,6 +163,13 @@ int cvm_decode_topk_semseg(const cvm_layout* L, const float* y_pred, int pred_st
                            float* scores, int32_t* cls, long long* flat, float* centers, float* boxes, float* track,
                            int seg_off, int seg_n, unsigned char* seg_ids, void* ws, size_t ws_bytes, void* stream);
 
+/* Monitoring.  cvm_decode_topk predicts each image's K-th best score from the image before it (and, through the workspace,
+ * from the previous call) so that only a few hundred pixels per image need the exact 3x3 test; the prediction is verified
+ * per image and an image it does not hold for is recomputed exactly by a slower path.  Results never depend on it.  This
+ * returns how many images (since the library was loaded, on the current device) took the slow path; it synchronises the
+ * device.  -1 on error. */
+long long cvm_decode_fallback_count(void);
+
 /* Profile R: window x window first-argmax (window odd, 9 in the reference) + strict threshold, scan order.
  * counts[B] = number of objects found (may exceed max_out; only the first max_out in scan order are written). */
 size_t cvm_decode_window9_workspace_bytes(const cvm_layout* L, int B);

@@ -26,3 +26,13 @@ names = ["scanner: wait full barrier", "scanner: wait first threshold (hint owne
          "batches", "test rounds", "peaks appended", "loader: wait free slot", "loader: total", "tester: gather at segment end", "scanner: wait lookahead granule", "tester: test preamble", "tester: window loads + vote", "tester: append", "scanner: scan (steady)", "scanner: push (steady)"]
 for n, x in zip(names, v):
     print(f"{n:48s} {x:16d}  per CTA {x / n_cta:14.1f}")
+
+import numpy as np
+ct = (C.c_ulonglong * 1024)()
+ops.decode_topk(L, yp, K=100)
+lib.cvm_decode_cta_times(ct)
+a = np.array(list(ct), dtype=np.int64).reshape(4, 256)[:, :n_cta]
+t0 = a[0].min()
+for i, nm in enumerate(["start", "loader done", "scanners done", "testers done"]):
+    r = (a[i] - t0) / 1000.0
+    print(f"{nm:14s} us: min {r.min():8.2f} median {np.median(r):8.2f} max {r.max():8.2f}")

@@ -26,7 +26,8 @@ def run(tag):
     for i in range(n): ops.decode_topk(L, yp if i % 2 else yp2, K=100)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    print(f"{tag:40s} {ms:.4f} ms  {yp.numel()*4/ms/1e6:.0f} GB/s", flush=True)
+    from cvmhot import _lib
+    print(f"{tag:40s} {ms:.4f} ms  {yp.numel()*4/ms/1e6:.0f} GB/s   slow-path images so far: {_lib.lib().cvm_decode_fallback_count()}", flush=True)
 for env in sys.argv[1:]:
     for kv in env.split(","):
         if kv and kv != "-":
