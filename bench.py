@@ -1,17 +1,24 @@
 #!/usr/bin/env python
-"""Benchmark of the CenterNet heatmap hot path (render + loss + decode) — BASELINE.json's metric.
+"""Benchmark of the CenterNet / CenterTracker heatmap hot path — BASELINE.json's metric.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|4|5] [--batch B] [--check]
 
-One "step" = one pass of the hot path over one batch of synthetic input of BASELINE.json configs[1]
-("CenterNet 2D-OD full heatmap path (render+loss+decode) batch 256 on 1xB200": 10 classes, 128x384 heatmaps, 32 objects per
-image, top-K = 100).  Under torchrun (N > 1) every rank owns its own 256 images (weak scaling; N = 8 is configs[2]'s
-2048-image batch), the only collective is the all-reduce of the 16 loss partials, timing is barrier + device events,
-max over ranks.  Rank 0 prints ONE JSON line.
+One "step" = one pass of the hot path over one batch of synthetic input per GPU:
 
-`--impl reference` times the reference's CPU implementation of the same path on the host cores: /root/reference (pure
-Python/numba/TF) cannot travel to the GPU box and TF is not installed, so this is the oracle port (oracle/: NumPy
-restatement; C + OpenMP restatement when built), on a bounded sample of the same workload.
+  --config 2 (default; BASELINE configs[1], and configs[2] at N = 8): render + loss + decode, 256 images per GPU, 10 classes,
+             128x384 heatmaps, 32 objects per image, top-K = 100 (11 403 264 algorithmic bytes per image)
+  --config 4 (BASELINE configs[3]): CenterTracker, 512 images: previous-frame heatmap render (1 channel, per-object peak)
+             + decode with the tracking-offset gather, 16-channel pixels (3 342 336 B per image)
+  --config 5 (BASELINE configs[4]): multitask head, 512x1536 maps, 128 images per GPU: CenterNet decode on channels [0:14]
+             + semseg argmax on channels [14:19] of the SAME 20-channel tensor in one read (63 700 992 B per image)
+
+Under torchrun (N > 1) every rank owns its own images (weak scaling), the only collective is the exchange of the 16 loss
+partials, timing is barrier + device events, max over ranks.  Rank 0 prints ONE JSON line.  --check (N > 1): the
+sharded loss partials are compared bit for bit with the same images processed shard by shard on ONE GPU.
+
+`--impl reference` times the reference's own CPU implementation of the same path on the host cores (oracle/ref_harness.py:
+the real numba fill_heatmap and to_3channel, the unmodified loss.py over the TF-on-torch shim, and - the reference has no
+top-K decode - the NumPy restatement of the canonical decode), one full batch per step where that is affordable.
 """
 import argparse
 import json
@@ -28,19 +35,30 @@ for _p in (ROOT, os.path.join(ROOT, "computer-vision-models_b200")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-H, W, NB_CLASSES, N_OBJ, TOPK = 128, 384, 10, 32, 100
+NB_CLASSES, N_OBJ, TOPK = 10, 32, 100
+CONFIGS = {
+    2: dict(H=128, W=384, batch=256, track=False, wide=0,
+            workload="CenterNet 2D-OD full heatmap path (render+loss+decode), 10-class 128x384, 32 obj/img, top-K=100 (BASELINE configs[1])"),
+    4: dict(H=128, W=384, batch=512, track=True, wide=0,
+            workload="CenterTracker: prev-frame heatmap render + decode with tracking-offset gather, 10-class 128x384, 16-channel pixels, "
+                     "32 obj/img, top-K=100 (BASELINE configs[3])"),
+    5: dict(H=512, W=1536, batch=128, track=False, wide=20,
+            workload="multitask head: CenterNet decode [0:14] + semseg argmax [14:19] of one 20-channel 512x1536 tensor, one read, "
+                     "top-K=100 (BASELINE configs[4]: 1024 images over 8 GPUs = 128 per GPU)"),
+}
+H, W = 128, 384          # (config 2 shape; kept as module attributes for the tests that import gen_objects)
 CONFIG_ID = 2
 
 
-def gen_objects(first_image, B):
+def gen_objects(first_image, B, Hm=H, Wm=W, config_id=CONFIG_ID):
     """per-image rng = default_rng(1234 + 1000*config + image_index); boxes in input px, inside the image."""
     R = 2
-    in_w, in_h = W * R, H * R
+    in_w, in_h = Wm * R, Hm * R
     boxes = np.zeros((B, N_OBJ, 4), np.float64)
     cls = np.zeros((B, N_OBJ), np.int32)
     ign = np.zeros((B, 2, 4), np.float64)
     for i in range(B):
-        rng = np.random.default_rng(1234 + 1000 * CONFIG_ID + first_image + i)
+        rng = np.random.default_rng(1234 + 1000 * config_id + first_image + i)
         w = np.exp(rng.uniform(np.log(4), np.log(160), N_OBJ))
         h = np.exp(rng.uniform(np.log(4), np.log(96), N_OBJ))
         cx, cy = rng.uniform(0, in_w, N_OBJ), rng.uniform(0, in_h, N_OBJ)
@@ -48,14 +66,29 @@ def gen_objects(first_image, B):
         x1, y1 = np.minimum(in_w, cx + w / 2), np.minimum(in_h, cy + h / 2)
         boxes[i] = np.stack([x0, y0, x1 - x0, y1 - y0], axis=1)
         cls[i] = rng.integers(0, NB_CLASSES, N_OBJ)
-        ign[i] = np.stack([rng.uniform(0, W - 4, 2), rng.uniform(0, H - 4, 2), rng.uniform(1, 12, 2), rng.uniform(1, 8, 2)], axis=1)
+        ign[i] = np.stack([rng.uniform(0, Wm - 4, 2), rng.uniform(0, Hm - 4, 2), rng.uniform(1, 12, 2), rng.uniform(1, 8, 2)], axis=1)
     return boxes, cls, ign
 
 
-def centres(boxes):
-    cx = np.clip(((boxes[..., 0] + boxes[..., 2] / 2) / 2).astype(np.int64), 0, W - 1)
-    cy = np.clip(((boxes[..., 1] + boxes[..., 3] / 2) / 2).astype(np.int64), 0, H - 1)
+def centres(boxes, Hm=H, Wm=W):
+    cx = np.clip(((boxes[..., 0] + boxes[..., 2] / 2) / 2).astype(np.int64), 0, Wm - 1)
+    cy = np.clip(((boxes[..., 1] + boxes[..., 3] / 2) / 2).astype(np.int64), 0, Hm - 1)
     return cx, cy
+
+
+def prev_records(boxes, first_image):
+    """Previous-frame blobs of config 4 (intended behaviour of centertracker/processor.py:22-41 with FN/FP off): one blob per
+    object at its (jittered) centre in mask px, size of the box, peak U(0.2, 0.7)."""
+    B = boxes.shape[0]
+    cx, cy = centres(boxes)
+    out = []
+    for i in range(B):
+        rng = np.random.default_rng(777 + first_image + i)
+        jx, jy = rng.integers(-2, 3, N_OBJ), rng.integers(-2, 3, N_OBJ)
+        peak = rng.uniform(0.2, 0.7, N_OBJ)
+        out.append([(int(cx[i, k] + jx[k]), int(cy[i, k] + jy[k]), float(boxes[i, k, 2]), float(boxes[i, k, 3]), float(peak[k]))
+                    for k in range(N_OBJ)])
+    return out
 
 
 class ClockSampler:
@@ -91,12 +124,13 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def load_traffic(kernel):
+def load_traffic(kernel, config_id):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed `ncu --set full` capture
     of this same workload (profiles/traffic.json, written by profiles/ncu_traffic.py); None if not captured."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
-        return json.load(open(p)).get(kernel)
+        d = json.load(open(p))
+        return d.get(f"config{config_id}", d if config_id == 2 else {}).get(kernel)
     return None
 
 
@@ -108,87 +142,176 @@ def load_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def _port_inputs(first_image, n_images):
+# the reference's CPU implementation of the path (test infrastructure: oracle/), used by --impl reference and cpu_baseline
+def _cpu_inputs(config_id, first_image, n_images):
+    """Host-side synthetic inputs of `n_images` images of the config (same distributions as the device-side generator)."""
     from oracle.layout import make_layout
-    Lo = make_layout(H, W, NB_CLASSES, "N")
-    boxes, cls, ign = gen_objects(first_image, n_images)
+    c = CONFIGS[config_id]
+    Hm, Wm = c["H"], c["W"]
+    Lo = make_layout(Hm, Wm, NB_CLASSES, "N", track=c["track"])
+    boxes, cls, ign = gen_objects(first_image, n_images, Hm, Wm, config_id)
     rng = np.random.default_rng(99 + first_image)
-    yp = np.zeros((n_images, H, W, Lo.Cp), np.float32)
-    yp[..., :NB_CLASSES] = 1.0 / (1.0 + np.exp(-rng.normal(-4.0, 1.5, (n_images, H, W, NB_CLASSES))))
-    yp[..., NB_CLASSES:] = rng.uniform(0, 60, (n_images, H, W, Lo.Cp - NB_CLASSES))
-    return Lo, boxes, cls, ign, yp
+    C = c["wide"] or Lo.Cp
+    yp = np.empty((n_images, Hm, Wm, C), np.float32)
+    yp[..., :NB_CLASSES] = 1.0 / (1.0 + np.exp(-rng.normal(-4.0, 1.5, (n_images, Hm, Wm, NB_CLASSES)).astype(np.float32)))
+    yp[..., NB_CLASSES:] = rng.uniform(0, 60, (n_images, Hm, Wm, C - NB_CLASSES)).astype(np.float32)
+    return dict(Lo=Lo, boxes=boxes, cls=cls, ign=ign, yp=yp, prev=prev_records(boxes, first_image) if c["track"] else None)
 
 
-def cpu_port_step(n_images, first_image=0, inputs=None):
-    """The oracle port of the path on `n_images` images of the same workload; returns seconds (render, loss, decode)
-    and the loss partials of these images."""
-    from oracle import decode_np, loss_np, render_np
-    Lo, boxes, cls, ign, yp = inputs if inputs is not None else _port_inputs(first_image, n_images)
+_REF = {}
+
+
+def _ref():
+    if not _REF:
+        from oracle import ref_import, ref_harness
+        _REF["r"] = ref_import.load()
+        _REF["h"] = ref_harness
+    return _REF["r"], _REF["h"]
+
+
+def cpu_render_decode(config_id, inp):
+    """Per-image stages of the reference path on one core: returns (seconds dict, y_true or None)."""
+    from oracle import decode_np
+    r, hz = _ref()
+    c = CONFIGS[config_id]
+    Lo, n = inp["Lo"], inp["yp"].shape[0]
+    t = {}
+    yt = None
     t0 = time.perf_counter()
-    yt = np.stack([render_np.render_image(Lo, boxes[i], cls[i], ign[i]) for i in range(n_images)])
-    t1 = time.perf_counter()
-    part = loss_np.partials(Lo, yt, yp, True)
-    t2 = time.perf_counter()
-    decode_np.decode_topk(Lo, yp, TOPK)
-    t3 = time.perf_counter()
-    return (t1 - t0, t2 - t1, t3 - t2), np.asarray(part, np.float64)
+    if config_id == 2:       # REAL fill_heatmap / calc_img_data, loop of processor.py:264-334
+        proc, P = hz.make_render_ctx(r, NB_CLASSES, NB_CLASSES, c["H"], c["W"])
+        yt = np.stack([hz.render_image_ref(r, proc, P, NB_CLASSES, c["H"], c["W"], inp["boxes"][i], inp["cls"][i], inp["ign"][i])
+                       for i in range(n)])
+    elif config_id == 4:     # REAL fill_heatmap with explicit centres and peaks (centertracker/processor.py:22-41)
+        for i in range(n):
+            hm = np.zeros((c["H"], c["W"], 1), np.float32)
+            wts = np.ones((c["H"], c["W"]), np.float32)
+            for cx, cy, w, h, peak in inp["prev"][i]:
+                r["fill_heatmap"](hm, 0.9, 2, wts, cx, cy, w, h, c["W"], c["H"], peak)
+    t["render"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    decode_np.decode_topk(Lo, inp["yp"][..., :Lo.Cp], TOPK)      # NumPy restatement (the reference has no top-K decode)
+    t["decode"] = time.perf_counter() - t0
+    if config_id == 5:       # REAL to_3channel (numba) on the semseg slice
+        from numba.typed import List
+        items = List([(k, v) for k, v in zip("abcde", [(32, 32, 64), (0, 0, 255), (96, 128, 128), (102, 255, 0), (255, 0, 204)])])
+        t0 = time.perf_counter()
+        for i in range(n):
+            r["to_3channel"](inp["yp"][i, ..., 14:19].copy(), items, None, False, False)
+        t["semseg"] = time.perf_counter() - t0
+    return t, yt
 
 
 _WORKER_INPUTS = {}
 
 
-def _port_worker(task):
-    """One host core's share of a reference-arm step (images are independent; the loss partials are summed by the parent,
-    which is the same exchange the GPUs do)."""
-    first, n = task
-    return cpu_port_step(n, first, _WORKER_INPUTS[(first, n)])   # inputs were generated by the parent before the fork
+def _cpu_worker(task):
+    config_id, key = task
+    return cpu_render_decode(config_id, _WORKER_INPUTS[key])
+
+
+def cpu_loss(inp, yt):
+    """The UNMODIFIED reference loss.py (CenternetLoss.call) executed over the TF-on-torch shim, all host threads."""
+    r, hz = _ref()
+    loss, _ = hz.ref_loss_object(r, NB_CLASSES, hm=NB_CLASSES)
+    t0 = time.perf_counter()
+    v = float(loss(yt, inp["yp"]))
+    return time.perf_counter() - t0, v
+
+
+def warm_reference(config_id):
+    """numba compilation and imports, outside every timed region."""
+    inp = _cpu_inputs(config_id, 0, 1) if config_id != 5 else None
+    if inp is not None:
+        _, yt = cpu_render_decode(config_id, inp)
+        if config_id == 2:
+            cpu_loss(inp, yt)
+    else:
+        r, _ = _ref()
+        from numba.typed import List
+        items = List([(k, v) for k, v in zip("abcde", [(32, 32, 64), (0, 0, 255), (96, 128, 128), (102, 255, 0), (255, 0, 204)])])
+        r["to_3channel"](np.zeros((4, 4, 5), np.float32), items, None, False, False)
 
 
 def run_reference(args):
-    """Reference arm: the reference's CPU implementation of the path on the host cores.  The reference itself (pure
-    Python on TensorFlow/numba, no setup.py) can be neither installed nor carried to the GPU box, so this is the oracle
-    port, spread over all host cores.  Under torchrun only rank 0 works."""
+    """Reference arm: the reference's CPU implementation of the path on ALL host cores.  Render / decode are per image
+    (a process pool, one share per core, inputs generated before the fork); the loss needs the whole batch (its counts
+    are batch-global) and runs in the parent with torch's intra-op threads.  Under torchrun only rank 0 works."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import multiprocessing as mp
-    from oracle import loss_np
-    from oracle.layout import make_layout
+    import torch
+    cfg = CONFIGS[args.config]
     cores = max(1, os.cpu_count() or 1)
-    per_core = 2
-    n = cores * per_core  # bounded sample per step
-    tasks = [(i * per_core, per_core) for i in range(cores)]
-    Lo = make_layout(H, W, NB_CLASSES, "N")
-    for t in tasks:                                          # synthetic inputs: generated once, outside the timed region
-        _WORKER_INPUTS[t] = _port_inputs(*t)
-    with mp.get_context("fork").Pool(cores) as pool:
+    torch.set_num_threads(cores)
+    # images per step: the full per-GPU batch where a step stays within seconds, else a bounded sample
+    n = {2: args.batch or cfg["batch"], 4: min(args.batch or cfg["batch"], 8 * cores), 5: min(args.batch or cfg["batch"], max(2, cores // 4))}[args.config]
+    shares = [list(range(i, n, cores)) for i in range(min(cores, n))]
+    sizes = [len(s) for s in shares]
+    firsts = np.concatenate([[0], np.cumsum(sizes)])[:-1]
+    for k, (f, sz) in enumerate(zip(firsts, sizes)):
+        _WORKER_INPUTS[k] = _cpu_inputs(args.config, int(f), sz)
+    warm_reference(args.config)
+    whole_yp = np.concatenate([_WORKER_INPUTS[k]["yp"] for k in range(len(shares))]) if args.config == 2 else None
+    stage = {}
+    loss_v = None
+    with mp.get_context("fork").Pool(len(shares)) as pool:
+        tasks = [(args.config, k) for k in range(len(shares))]
         for _ in range(max(args.warmup, 1)):
-            pool.map(_port_worker, tasks, chunksize=1)
+            pool.map(_cpu_worker, tasks, chunksize=1)
         t0 = time.perf_counter()
-        stage = np.zeros(3)
         for _ in range(args.steps):
-            res = pool.map(_port_worker, tasks, chunksize=1)
-            part = np.sum([r[1] for r in res], axis=0)      # the one exchange of the path, then the finalise step
-            loss = loss_np.finalize(Lo, part.tolist())[0]
-            stage += np.sum([r[0] for r in res], axis=0)
+            res = pool.map(_cpu_worker, tasks, chunksize=1)
+            for tt, _ in res:
+                for k, v in tt.items():
+                    stage[k] = stage.get(k, 0.0) + v
+            if args.config == 2:
+                yt = np.concatenate([r_[1] for r_ in res])
+                dt, loss_v = cpu_loss(dict(yp=whole_yp), yt)
+                stage["loss_wall"] = stage.get("loss_wall", 0.0) + dt
         tot = time.perf_counter() - t0
     value = n * args.steps / tot
+    same = n == (args.batch or cfg["batch"])
+    kinds = {2: "reference (real numba fill_heatmap + unmodified loss.py over the TF-on-torch shim) + port (NumPy top-K decode: the reference has none)",
+             4: "reference (real numba fill_heatmap) + port (NumPy top-K decode with track gather)",
+             5: "reference (real numba to_3channel) + port (NumPy top-K decode)"}[args.config]
     line = {
         "impl": "reference", "metric": "images/sec (heatmap render+loss+decode)", "value": value, "unit": "images/sec",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * tot / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CenterNet 2D-OD full heatmap path (render+loss+decode), 10-class 128x384, 32 obj/img, top-K=100 (BASELINE configs[1])",
-                   "batch_per_step": n, "note": "bounded sample of configs[1] (same per-image work)"},
-        "cpu_baseline": {"value": value, "unit": "images/sec", "cores": cores, "kind": "port",
-                         "sample": f"{n} images/step x {args.steps} steps, NumPy oracle port over {cores} worker processes "
-                                   "(the TF/numba reference cannot be installed or carried to the box)"},
+        "config": {"workload": cfg["workload"], "batch_per_step": n,
+                   "note": "the full per-GPU batch per step" if same else "bounded sample of the per-GPU batch (same per-image work)"},
+        "cpu_baseline": {"value": value, "unit": "images/sec", "cores": cores, "kind": "reference",
+                         "sample": f"{n} images/step x {args.steps} steps on {cores} host cores; {kinds}"},
         "e2e": {"value": value, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "stages_core_s_per_image": {k: float(stage[i] / (n * args.steps)) for i, k in enumerate(("render", "loss", "decode"))},
-        "loss": float(loss),
+        "stages_core_s_per_image": {k: float(v / (n * args.steps)) for k, v in stage.items()},
+        "loss": loss_v,
     }
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def make_pred(torch, dev, g, B, Hm, Wm, L, C_total, boxes, cls):
+    """Synthetic y_pred on the device: sigmoid-noise heatmaps with the object centres raised, heads filled."""
+    y_pred = torch.empty((B, Hm, Wm, C_total), dtype=torch.float32, device=dev)
+    chunk = max(1, min(B, (1 << 28) // (Hm * Wm * C_total)))       # bounded temporaries for the large maps
+    for a in range(0, B, chunk):
+        b = min(B, a + chunk)
+        y_pred[a:b, ..., :L.hm] = torch.sigmoid(torch.randn((b - a, Hm, Wm, L.hm), device=dev, generator=g) * 1.5 - 4.0)
+        y_pred[a:b, ..., L.off_roff:L.off_roff + 2] = torch.rand((b - a, Hm, Wm, 2), device=dev, generator=g)
+        y_pred[a:b, ..., L.off_box:L.off_box + 2] = torch.rand((b - a, Hm, Wm, 2), device=dev, generator=g) * 120 + 4
+        if L.off_track >= 0:
+            y_pred[a:b, ..., L.off_track:L.off_track + 2] = torch.randn((b - a, Hm, Wm, 2), device=dev, generator=g) * 8
+        if C_total > L.Cp:
+            y_pred[a:b, ..., L.Cp:] = torch.randn((b - a, Hm, Wm, C_total - L.Cp), device=dev, generator=g)
+    cx, cy = centres(boxes, Hm, Wm)
+    bi = np.repeat(np.arange(B), N_OBJ)
+    peak = torch.rand(B * N_OBJ, device=dev, generator=g) * 0.69 + 0.3
+    y_pred[torch.from_numpy(bi).to(dev), torch.from_numpy(cy.reshape(-1)).to(dev), torch.from_numpy(cx.reshape(-1)).to(dev),
+           torch.from_numpy(cls.reshape(-1).astype(np.int64)).to(dev)] = peak
+    return y_pred
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -196,66 +319,101 @@ def run_ours(args):
     from cvmhot import ops
     from cvmhot.layout import layout_from_params
     from cvmhot.models.centernet import CenternetParams
+    from cvmhot.models.centertracker import CentertrackerParams, CenterTrackerProcess
     from cvmhot.models.centernet.processor import pack_boxes, pack_objects
 
     rank, world, local = cdist.init_from_env()
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    B = args.batch
+    cfg = CONFIGS[args.config]
+    Hm, Wm = cfg["H"], cfg["W"]
+    B = args.batch or cfg["batch"]
 
-    p = CenternetParams(NB_CLASSES, per_class_heatmap=True)
-    p.INPUT_HEIGHT, p.INPUT_WIDTH = H * 2, W * 2
+    p = (CentertrackerParams if cfg["track"] else CenternetParams)(NB_CLASSES, per_class_heatmap=True)
+    p.INPUT_HEIGHT, p.INPUT_WIDTH = Hm * 2, Wm * 2
     L = layout_from_params(p)
-    assert (L.Cp, L.Ct) == (14, 15)
+    C_total = cfg["wide"] or L.Cp
+    assert L.Cp == (16 if cfg["track"] else 14)
 
     # ---- synthetic inputs, resident in HBM before the timed region ----
-    boxes, cls, ign = gen_objects(rank * B, B)
-    rec, offs = pack_objects(list(boxes), list(cls))
-    ign_rec, ign_offs = pack_boxes(list(ign))
-    objs_d = ops.to_device_records(rec, ops.OBJ_DTYPE, dev)
-    offs_d = torch.from_numpy(offs).to(dev)
-    ign_d = ops.to_device_records(ign_rec, ops.BOX_DTYPE, dev)
-    ioffs_d = torch.from_numpy(ign_offs).to(dev)
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    y_pred = torch.empty((B, H, W, L.Cp), dtype=torch.float32, device=dev)
-    y_pred[..., :L.hm] = torch.sigmoid(torch.randn((B, H, W, L.hm), device=dev, generator=g) * 1.5 - 4.0)
-    y_pred[..., L.off_roff:L.off_roff + 2] = torch.rand((B, H, W, 2), device=dev, generator=g)
-    y_pred[..., L.off_box:L.off_box + 2] = torch.rand((B, H, W, 2), device=dev, generator=g) * 120 + 4
-    cx, cy = centres(boxes)
-    bi = np.repeat(np.arange(B), N_OBJ)
-    peak = torch.rand(B * N_OBJ, device=dev, generator=g) * 0.69 + 0.3
-    y_pred[torch.from_numpy(bi).to(dev), torch.from_numpy(cy.reshape(-1)).to(dev), torch.from_numpy(cx.reshape(-1)).to(dev),
-           torch.from_numpy(cls.reshape(-1).astype(np.int64)).to(dev)] = peak
-    y_true = torch.empty((B, H, W, L.Ct), dtype=torch.float32, device=dev)
-    partials = torch.empty(16, dtype=torch.float64, device=dev)
-    loss_out = torch.zeros(10, dtype=torch.float32, device=dev)
+    def device_inputs(first_image, seed):
+        boxes, cls, ign = gen_objects(first_image, B, Hm, Wm, args.config)
+        g = torch.Generator(device=dev).manual_seed(seed)
+        d = dict(boxes=boxes, cls=cls, ign=ign, y_pred=make_pred(torch, dev, g, B, Hm, Wm, L, C_total, boxes, cls))
+        if args.config == 2:
+            d["rec"], d["offs"] = pack_objects(list(boxes), list(cls))
+            d["ign_rec"], d["ign_offs"] = pack_boxes(list(ign))
+        if args.config == 4:
+            d["rec"], d["offs"] = CenterTrackerProcess.pack_prev_records(prev_records(boxes, first_image))
+        if "rec" in d:
+            d["objs_d"] = ops.to_device_records(d["rec"], ops.OBJ_DTYPE, dev)
+            d["offs_d"] = torch.from_numpy(d["offs"]).to(dev)
+        if "ign_rec" in d:
+            d["ign_d"] = ops.to_device_records(d["ign_rec"], ops.BOX_DTYPE, dev)
+            d["ioffs_d"] = torch.from_numpy(d["ign_offs"]).to(dev)
+        return d
 
-    bytes_render = 4 * H * W * L.Ct * B
-    bytes_loss = 4 * H * W * (L.Ct + L.Cp) * B
-    bytes_decode = 4 * H * W * L.Cp * B
+    inp = device_inputs(rank * B, 1234 + rank)
+    y_pred = inp["y_pred"]
+    y_pred_cn = y_pred[..., :L.Cp]                       # (config 5: the CenterNet slice of the wide tensor, read in place)
+    y_true = torch.empty((B, Hm, Wm, L.Ct), dtype=torch.float32, device=dev) if args.config == 2 else None
+    prev_hm = torch.empty((B, Hm, Wm, 1), dtype=torch.float32, device=dev) if args.config == 4 else None
+    partials = torch.empty(16, dtype=torch.float64, device=dev)
+    gathered = torch.empty((world, 16), dtype=torch.float64, device=dev)
+    loss_out = torch.zeros(10, dtype=torch.float32, device=dev)
+    px = Hm * Wm
+    if args.config == 2:
+        names = ["render_kernel", "loss_fwd_fast_kernel", "decode_scan_kernel"]
+        sbytes = [4 * px * L.Ct * B, 4 * px * (L.Ct + L.Cp) * B, 4 * px * L.Cp * B]
+        launches = 4 if world == 1 else 5      # render, loss (+ reduce + finalize in its last block), scan, merge (+ finalize at N > 1)
+    elif args.config == 4:
+        names = ["render_kernel(prev_hm)", "decode_scan_kernel"]
+        sbytes = [4 * px * B, 4 * px * L.Cp * B]
+        launches = 3
+    else:
+        names = ["decode_scan_kernel(+semseg argmax)"]
+        sbytes = [(4 * px * C_total + px) * B]
+        launches = 2
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def step(events=None):
-        if events is not None:
-            events[0].record()
-        ops.render_gt(L, objs_d, offs_d, B, ign_d, ioffs_d, out=y_true)
-        if events is not None:
-            events[1].record()
-        ops.loss_partials(L, y_true, y_pred, True, out=partials)
-        # the one collective of the path: 16 doubles, summed over the ranks while the decode kernel runs
-        work = dist.all_reduce(partials, async_op=True) if world > 1 else None
-        if events is not None:
-            events[2].record()
-        out = ops.decode_topk(L, y_pred, K=TOPK)
-        if work is not None:
-            work.wait()
-        ops.loss_finalize(L, partials, out=loss_out)
-        if events is not None:
-            events[3].record()
+        k = 0
+
+        def mark():
+            nonlocal k
+            if events is not None:
+                events[k].record()
+            k += 1
+        mark()
+        out = None
+        if args.config == 2:
+            ops.render_gt(L, inp["objs_d"], inp["offs_d"], B, inp["ign_d"], inp["ioffs_d"], out=y_true)
+            mark()
+            if world == 1:
+                ops.loss_total(L, y_true, y_pred, True, partials=partials, out=loss_out)     # one launch
+                mark()
+                out = ops.decode_topk(L, y_pred, K=TOPK)
+            else:
+                ops.loss_partials(L, y_true, y_pred, True, out=partials)
+                # the one collective of the path: 16 doubles per rank, gathered while the decode kernel runs and summed in
+                # rank order (bit-reproducible whatever the collective's algorithm)
+                work = dist.all_gather_into_tensor(gathered.view(-1), partials, async_op=True)
+                mark()
+                out = ops.decode_topk(L, y_pred, K=TOPK)
+                work.wait()
+                ops.loss_finalize_gathered(L, gathered, partials=partials, out=loss_out)     # rank-ordered sum + finalise: one launch
+        elif args.config == 4:
+            ops.render_prev_heatmap(L, inp["objs_d"], inp["offs_d"], B, out=prev_hm)
+            mark()
+            out = ops.decode_topk(L, y_pred, K=TOPK)
+        else:
+            out = ops.decode_topk(L, y_pred_cn, K=TOPK, semseg=(14, 5))
+        mark()
         return out
 
+    n_marks = len(names) + 1
     for _ in range(max(args.warmup, 3)):
         out = step()
     torch.cuda.synchronize()
@@ -269,7 +427,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    stage_events = [[ev() for _ in range(4)] for _ in range(args.steps)]
+    stage_events = [[ev() for _ in range(n_marks)] for _ in range(args.steps)]
     barrier()
     e0, e1 = ev(), ev()
     e0.record()
@@ -278,24 +436,60 @@ def run_ours(args):
     e1.record()
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
-    stage_ms = np.array([[s[i].elapsed_time(s[i + 1]) for i in range(3)] for s in stage_events]).mean(axis=0)
+    stage_ms = np.array([[s[i].elapsed_time(s[i + 1]) for i in range(n_marks - 1)] for s in stage_events]).mean(axis=0)
+
+    # ---- the backward of the loss as its own timed stage (config 2; not part of the metric: reads y_true + y_pred, writes the gradient) ----
+    extra = {}
+    if args.config == 2:
+        grad = torch.empty_like(y_pred)
+        for _ in range(3):
+            ops.loss_backward(L, y_true, y_pred, partials, out=grad)
+        b0, b1 = ev(), ev()
+        torch.cuda.synchronize()
+        b0.record()
+        for _ in range(args.steps):
+            ops.loss_backward(L, y_true, y_pred, partials, out=grad)
+        b1.record()
+        torch.cuda.synchronize()
+        bwd_ms = b0.elapsed_time(b1) / args.steps
+        bwd_bytes = 4 * px * (L.Ct + 2 * L.Cp) * B
+        extra["loss_bwd_fast_kernel"] = {"ms": bwd_ms, "bytes": bwd_bytes}
+        del grad
+
+    # ---- --check: the sharded partials equal the same images processed shard by shard on one GPU, bit for bit ----
+    check = None
+    if args.check and args.config == 2:
+        mine = partials.clone()
+        shard_parts = []
+        for r_ in range(world):
+            o = inp if r_ == rank else device_inputs(r_ * B, 1234 + r_)
+            yt_r = torch.empty_like(y_true)
+            ops.render_gt(L, o["objs_d"], o["offs_d"], B, o["ign_d"], o["ioffs_d"], out=yt_r)
+            shard_parts.append(ops.loss_partials(L, yt_r, o["y_pred"], True).clone())
+            del yt_r
+            if r_ != rank:
+                del o
+        single = cdist.ordered_sum(torch.stack(shard_parts))
+        ok = torch.tensor([1.0 if torch.equal(single, mine) else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        check = {"sharded_partials_equal_single_gpu_bitwise": bool(ok.item() == 1.0), "ranks": world, "images": world * B}
 
     # ---- e2e: the same step through the public API with HOST buffers (pinned), copies inside the timed region ----
-    rec_h = torch.from_numpy(rec.view(np.uint8).reshape(-1)).pin_memory()
-    ign_h = torch.from_numpy(ign_rec.view(np.uint8).reshape(-1)).pin_memory()
-    offs_h, ioffs_h = torch.from_numpy(offs).pin_memory(), torch.from_numpy(ign_offs).pin_memory()
-    y_pred_h = torch.empty(y_pred.shape, dtype=torch.float32).pin_memory()
-    y_pred_h.copy_(y_pred)
+    e2e_steps = max(2, min(args.steps, 5 if args.config != 5 else 2))
     res_h = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items() if v is not None}
     loss_h = torch.empty(10, dtype=torch.float32).pin_memory()
-    h2d = rec_h.numel() + ign_h.numel() + offs_h.numel() * 4 + ioffs_h.numel() * 4 + y_pred_h.numel() * 4
-    d2h = loss_h.numel() * 4 + sum(v.numel() * v.element_size() for v in res_h.values())
+    y_pred_h = torch.empty(y_pred.shape, dtype=torch.float32).pin_memory()
+    y_pred_h.copy_(y_pred)
+    small_h = {k: torch.from_numpy(v.view(np.uint8).reshape(-1) if v.dtype.fields else v).pin_memory()
+               for k, v in inp.items() if k in ("rec", "offs", "ign_rec", "ign_offs")}
+    h2d = y_pred_h.numel() * 4 + sum(v.numel() * v.element_size() for v in small_h.values())
+    d2h = sum(v.numel() * v.element_size() for v in res_h.values()) + (loss_h.numel() * 4 if args.config == 2 else 0)
     y_pred_in = torch.empty_like(y_pred)
 
-    # The 705 MB of y_pred dominate the step (PCIe), so the batch is cut into chunks whose host->device copies run on a
-    # copy stream while the previous chunk is in the kernels: loss partials are additive over chunks (summed before the one
-    # all-reduce), render and decode are per image.
-    n_chunks = 4
+    # y_pred dominates the step (PCIe), so the batch is cut into chunks whose host->device copies run on a copy stream while
+    # the previous chunk is in the kernels: loss partials are additive over chunks, render and decode are per image.
+    n_chunks = args.chunks
     bounds = [(k * B // n_chunks, (k + 1) * B // n_chunks) for k in range(n_chunks)]
     copy_stream = torch.cuda.Stream(device=dev)
     chunk_partials = torch.empty((n_chunks, 16), dtype=torch.float64, device=dev)
@@ -310,27 +504,29 @@ def run_ours(args):
                 e = torch.cuda.Event()
                 e.record(copy_stream)
                 ready.append(e)
-        o_d = rec_h.to(dev, non_blocking=True)
-        of_d = offs_h.to(dev, non_blocking=True)
-        i_d = ign_h.to(dev, non_blocking=True)
-        if_d = ioffs_h.to(dev, non_blocking=True)
-        ops.render_gt(L, o_d, of_d, B, i_d, if_d, out=y_true)
+        sd = {k: v.to(dev, non_blocking=True) for k, v in small_h.items()}
+        if args.config == 2:
+            ops.render_gt(L, sd["rec"], sd["offs"], B, sd["ign_rec"], sd["ign_offs"], out=y_true)
+        elif args.config == 4:
+            ops.render_prev_heatmap(L, sd["rec"], sd["offs"], B, out=prev_hm)
         outs = []
         for k, (a, b) in enumerate(bounds):
             main.wait_event(ready[k])
-            ops.loss_partials(L, y_true[a:b], y_pred_in[a:b], True, out=chunk_partials[k])
-            outs.append(ops.decode_topk(L, y_pred_in[a:b], K=TOPK))
-        torch.sum(chunk_partials, dim=0, out=partials)
-        work = dist.all_reduce(partials, async_op=True) if world > 1 else None
+            if args.config == 2:
+                ops.loss_partials(L, y_true[a:b], y_pred_in[a:b], True, out=chunk_partials[k])
+            outs.append(ops.decode_topk(L, y_pred_in[a:b, ..., :L.Cp], K=TOPK, semseg=(14, 5) if args.config == 5 else None))
+        if args.config == 2:
+            cdist.ordered_sum(chunk_partials, out=partials)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered.view(-1), partials)
+                ops.loss_finalize_gathered(L, gathered, partials=partials, out=loss_out)
+            else:
+                ops.loss_finalize(L, partials, out=loss_out)
+            loss_h.copy_(loss_out, non_blocking=True)
         for k, (a, b) in enumerate(bounds):
             for k_, v in res_h.items():
                 v[a:b].copy_(outs[k][k_], non_blocking=True)
-        if work is not None:
-            work.wait()
-        ops.loss_finalize(L, partials, out=loss_out)
-        loss_h.copy_(loss_out, non_blocking=True)
 
-    e2e_steps = max(2, min(args.steps, 5))
     e2e_step()
     barrier()
     f0, f1 = ev(), ev()
@@ -354,41 +550,54 @@ def run_ours(args):
     value = world * B * args.steps / (elapsed_ms * 1e-3)
     e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
     peak_gbs, peak_src = load_peaks()
-    names = ["render_kernel", "loss_fwd_fast_kernel", "decode_scan_kernel"]
-    sbytes = [bytes_render, bytes_loss, bytes_decode]
     dom = int(np.argmax(stage_ms))
     achieved = sbytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
     whole = sum(sbytes) / (elapsed_ms / args.steps * 1e-3) / 1e9
+    stages = {n: {"ms": float(m), "gbs": b / (m * 1e-3) / 1e9, "frac": b / (m * 1e-3) / 1e9 / peak_gbs}
+              for n, m, b in zip(names, stage_ms, sbytes)}
+    for n, v in extra.items():
+        stages[n] = {"ms": v["ms"], "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9, "frac": v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak_gbs,
+                     "note": "timed on its own after the step loop; not part of `value`"}
 
-    # CPU baseline (reported only): oracle port on a bounded sample, rank 0, N = 1 only
+    # CPU baseline (reported only): the reference path on a bounded sample, ONE core, rank 0, N = 1 only
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        n_cpu = 8
-        cpu_port_step(1)
-        ts, _ = cpu_port_step(n_cpu)
-        cpu = {"value": n_cpu / sum(ts), "unit": "images/sec", "cores": 1, "kind": "port",
-               "sample": f"{n_cpu} images of the same workload (configs[0] batch), NumPy oracle port; "
-                         f"render {ts[0]:.2f}s loss {ts[1]:.2f}s decode {ts[2]:.2f}s"}
+        n_cpu = {2: 8, 4: 8, 5: 1}[args.config]
+        warm_reference(args.config)
+        ci = _cpu_inputs(args.config, 0, n_cpu)
+        import torch as _t
+        nt = _t.get_num_threads()
+        _t.set_num_threads(1)
+        ts, yt = cpu_render_decode(args.config, ci)
+        if args.config == 2:
+            ts["loss"] = cpu_loss(ci, yt)[0]
+        _t.set_num_threads(nt)
+        cpu = {"value": n_cpu / sum(ts.values()), "unit": "images/sec", "cores": 1, "kind": "reference",
+               "sample": f"{n_cpu} images of the same workload; real numba fill_heatmap / to_3channel, the unmodified loss.py over the "
+                         f"TF-on-torch shim, NumPy top-K decode (the reference has none); " + " ".join(f"{k} {v:.2f}s" for k, v in ts.items())}
 
     line = {
         "metric": "images/sec (heatmap render+loss+decode)", "value": value, "unit": "images/sec", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CenterNet 2D-OD full heatmap path (render+loss+decode), 10-class 128x384, 32 obj/img, top-K=100 (BASELINE configs[1])",
-                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world} (batch shards, one 128-byte all-reduce overlapped with decode)",
-                   "l2": "inputs larger than L2 (y_pred 705 MB + y_true 755 MB per GPU per step)"},
+        "config": {"workload": cfg["workload"], "batch_per_gpu": B, "global_batch": B * world,
+                   "parallelism": f"dp{world} (batch shards" + (", one 128-byte exchange overlapped with decode)" if args.config == 2 else ", no collective)"),
+                   "l2": f"inputs larger than L2 ({y_pred.numel() * 4 / 1e6:.0f} MB y_pred per GPU per step)"},
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": achieved / peak_gbs, "traffic": load_traffic(names[dom]), "peak_source": peak_src,
-                     "whole_step_gbs": whole, "whole_step_frac": whole / peak_gbs,
-                     "stages": {n: {"ms": float(m), "gbs": b / (m * 1e-3) / 1e9, "frac": b / (m * 1e-3) / 1e9 / peak_gbs}
-                                for n, m, b in zip(names, stage_ms, sbytes)}},
+                     "frac": achieved / peak_gbs, "traffic": load_traffic(names[dom].split("(")[0], args.config), "peak_source": peak_src,
+                     "whole_step_gbs": whole, "whole_step_frac": whole / peak_gbs, "stages": stages},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "note": "host pinned buffers -> public API -> host results, copies inside the timed region (4 chunks: H2D of chunk k+1 overlaps the kernels of chunk k)"},
-        "gpu_launches": 6 * args.steps,
+                "steps": e2e_steps, "note": f"host pinned buffers -> public API -> host results, copies inside the timed region "
+                                             f"({n_chunks} chunks: H2D of chunk k+1 overlaps the kernels of chunk k)"},
+        "gpu_launches": launches * args.steps,
         "clocks": clocks,
-        "loss": float(loss_out[0]),
+        "decode_slow_path_images": int(ops.decode_fallback_count()),
     }
+    if args.config == 2:
+        line["loss"] = float(loss_out[0])
+    if check is not None:
+        line["check"] = check
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -400,7 +609,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5], help="BASELINE.json configs[config-1]")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
+    ap.add_argument("--chunks", type=int, default=4, help="e2e leg: H2D chunks per step")
+    ap.add_argument("--check", action="store_true", help="N > 1: compare the sharded loss partials with one GPU, bit for bit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

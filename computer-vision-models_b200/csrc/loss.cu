@@ -36,6 +36,13 @@ struct LossParams {
     int use_bulk;
     int n_stages;      // ring depth of the fast kernel
     double* block_partials;   // [gridDim.x][CVM_NPART]
+    // the last block to finish sums the block partials in a fixed order (bit-reproducible) into `partials` and, when `fin_out`
+    // is given (single-GPU callers: nothing to all-reduce), applies the finalise step right away: no extra launches
+    unsigned int* ticket;     // zeroed by the host before the launch
+    double* partials;         // [CVM_NPART]
+    float* fin_out;           // [2 + CVM_MAX_FIELDS] or NULL
+    int fin_post[CVM_MAX_FIELDS];
+    float fin_weight[CVM_MAX_FIELDS];
 };
 
 __device__ __forceinline__ float pow_a(float x, const LossParams& p) { return p.a_is2 ? x * x : powf(x, p.fa); }
@@ -87,6 +94,56 @@ __device__ double field_term(int kind, const float* t, const float* q, int size)
             s += fabs(d / fmax(fabs((double)t[k]), 1.0));
     }
     return s;
+}
+
+// loss.py:59 (tf.cond n>0), :130, :98 (orientation), :140-153 (weighting); one thread
+__device__ void finalize_terms(const double* part, float* out, int n_fields, const int* f_post, const float* f_weight) {
+    const double P = part[0], N = part[1], n = part[2], nobj = part[3];
+    const double focal = n > 0.0 ? (P + N) / n : N;
+    double total = focal;
+    out[1] = (float)focal;
+    for (int f = 0; f < n_fields; ++f) {
+        double v = nobj > 0.0 ? part[4 + f] / nobj : part[4 + f];
+        if (f_post[f] == CVM_POST_ORIENT) v = sqrt(1.0 - 0.99 * cos(2.0 * v)) + fabs(v * v * 0.05) - 0.0999;
+        out[2 + f] = (float)v;
+        total += v * (double)f_weight[f];
+    }
+    out[0] = (float)total;
+}
+
+// Called by every thread of a block after it has written its block partials: the last block of the grid to get here
+// reduces all of them - 16 groups of blocks, then the groups, always in the same order, so the sums are bit-reproducible
+// run to run whichever block comes last - and writes partials[CVM_NPART] (and the finalised terms).  NT = block size.
+template <int NT>
+__device__ __forceinline__ void last_block_reduce(const LossParams& p) {
+    __shared__ double sh[16][CVM_NPART];
+    __shared__ int s_last;
+    __threadfence();            // this block's partials are visible device-wide before its ticket is
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int n_blocks = (int)gridDim.x;
+    const volatile double* bp = p.block_partials;
+    for (int t = threadIdx.x; t < 16 * CVM_NPART; t += NT) {
+        const int k = t % CVM_NPART, g = t / CVM_NPART;
+        double r = 0.0;
+        for (int b = g; b < n_blocks; b += 16) r += bp[(size_t)b * CVM_NPART + k];
+        sh[g][k] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < CVM_NPART) {
+        double t = 0.0;
+        for (int gi = 0; gi < 16; ++gi) t += sh[gi][threadIdx.x];
+        p.partials[threadIdx.x] = t;
+        sh[0][threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (p.fin_out) finalize_terms(&sh[0][0], p.fin_out, p.n_fields, p.fin_post, p.fin_weight);
+        *p.ticket = 0u;         // (the host zeroes it as well: a caller may hand over an uninitialised workspace)
+    }
 }
 
 __global__ void __launch_bounds__(kThreads) loss_fwd_kernel(const LossParams p) {
@@ -222,22 +279,7 @@ __global__ void __launch_bounds__(kThreads) loss_fwd_kernel(const LossParams p) 
         for (int wi = 0; wi < kThreads / 32; ++wi) r += red[wi][tid];
         p.block_partials[(size_t)blockIdx.x * CVM_NPART + tid] = r;
     }
-}
-
-// fixed-order reduction of the per-block partials -> partials[CVM_NPART]
-__global__ void __launch_bounds__(256) loss_reduce_kernel(const double* __restrict__ block_partials, int n_blocks,
-                                                          double* __restrict__ partials) {
-    __shared__ double sh[16][CVM_NPART];
-    const int k = threadIdx.x % CVM_NPART, g = threadIdx.x / CVM_NPART;  // 16 groups
-    double r = 0.0;
-    for (int b = g; b < n_blocks; b += 16) r += block_partials[(size_t)b * CVM_NPART + k];
-    sh[g][k] = r;
-    __syncthreads();
-    if (threadIdx.x < CVM_NPART) {
-        double t = 0.0;
-        for (int gi = 0; gi < 16; ++gi) t += sh[gi][threadIdx.x];
-        partials[threadIdx.x] = t;
-    }
+    last_block_reduce<kThreads>(p);
 }
 
 struct FinalizeParams {
@@ -246,20 +288,9 @@ struct FinalizeParams {
     float f_weight[CVM_MAX_FIELDS];
 };
 
-// loss.py:59 (tf.cond n>0), :130, :98 (orientation), :140-153 (weighting)
 __global__ void loss_finalize_kernel(const double* __restrict__ part, float* __restrict__ out, const FinalizeParams fp) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const double P = part[0], N = part[1], n = part[2], nobj = part[3];
-    const double focal = n > 0.0 ? (P + N) / n : N;
-    double total = focal;
-    out[1] = (float)focal;
-    for (int f = 0; f < fp.n_fields; ++f) {
-        double v = nobj > 0.0 ? part[4 + f] / nobj : part[4 + f];
-        if (fp.f_post[f] == CVM_POST_ORIENT) v = sqrt(1.0 - 0.99 * cos(2.0 * v)) + fabs(v * v * 0.05) - 0.0999;
-        out[2 + f] = (float)v;
-        total += v * (double)fp.f_weight[f];
-    }
-    out[0] = (float)total;
+    finalize_terms(part, out, fp.n_fields, fp.f_post, fp.f_weight);
 }
 
 int pick_span_pixels(int st_t, int st_p, size_t* smem_bytes) {
@@ -504,6 +535,7 @@ __global__ void __launch_bounds__(kFastThreads + 32) loss_fwd_fast_kernel(const 
         for (int wi = 0; wi < kConsumerWarps; ++wi) r += red[wi][tid];
         p.block_partials[(size_t)blockIdx.x * CVM_NPART + tid] = r;
     }
+    last_block_reduce<kFastThreads + 32>(p);
 }
 
 template <int HM, int ST_T, int ST_P>
@@ -544,13 +576,13 @@ int check_layout_for_loss(const cvm_layout* L, int st_t, int st_p) {
 extern "C" size_t cvm_loss_workspace_bytes(const cvm_layout* L, long long n_pixels) {
     (void)L;
     (void)n_pixels;
-    // per-block partials for the largest grid we ever launch (4 CTAs/SM)
-    return (size_t)cvm_num_sms() * 4 * CVM_NPART * sizeof(double);
+    // per-block partials for the largest grid we ever launch (4 CTAs/SM) + the ticket of the last-block reduction
+    return (size_t)cvm_num_sms() * 4 * CVM_NPART * sizeof(double) + 16;
 }
 
-extern "C" int cvm_loss_fwd(const cvm_layout* L, const float* y_true, int y_true_stride, const float* y_pred,
-                            int y_pred_stride, long long n_pixels, int use_weights, double* partials, void* ws,
-                            size_t ws_bytes, void* stream) {
+namespace {
+int loss_fwd_impl(const cvm_layout* L, const float* y_true, int y_true_stride, const float* y_pred, int y_pred_stride,
+                  long long n_pixels, int use_weights, double* partials, float* fin_out, void* ws, size_t ws_bytes, void* stream) {
     int rc = check_layout_for_loss(L, y_true_stride, y_pred_stride);
     if (rc != CVM_OK) return rc;
     CVM_CHECK_ARG(y_true && y_pred && partials && ws, "NULL pointer argument");
@@ -586,6 +618,14 @@ extern "C" int cvm_loss_fwd(const cvm_layout* L, const float* y_true, int y_true
     }
     p.use_bulk = cvm_aligned16(y_true) && cvm_aligned16(y_pred);
     p.block_partials = static_cast<double*>(ws);
+    p.ticket = reinterpret_cast<unsigned int*>(static_cast<unsigned char*>(ws) + (size_t)cvm_num_sms() * 4 * CVM_NPART * sizeof(double));
+    p.partials = partials;
+    p.fin_out = fin_out;
+    for (int f = 0; f < L->n_fields; ++f) {
+        p.fin_post[f] = L->field_post[f];
+        p.fin_weight[f] = L->field_weight[f];
+    }
+    CVM_CHECK_CUDA(cudaMemsetAsync(p.ticket, 0, 4, st));   // (a memset node, not a launch; the workspace may be uninitialised)
 
     int grid = 0;
     // compile-time layouts: (hm, y_true stride, y_pred stride) of BASELINE.json's configs and the reference defaults
@@ -607,8 +647,53 @@ extern "C" int cvm_loss_fwd(const cvm_layout* L, const float* y_true, int y_true
         loss_fwd_kernel<<<grid, kThreads, smem, st>>>(p);
         CVM_CHECK_LAUNCH("loss_fwd_kernel");
     }
-    loss_reduce_kernel<<<1, 256, 0, st>>>(p.block_partials, grid, partials);
-    CVM_CHECK_LAUNCH("loss_reduce_kernel");
+    return CVM_OK;
+}
+}  // namespace
+
+extern "C" int cvm_loss_fwd(const cvm_layout* L, const float* y_true, int y_true_stride, const float* y_pred,
+                            int y_pred_stride, long long n_pixels, int use_weights, double* partials, void* ws,
+                            size_t ws_bytes, void* stream) {
+    return loss_fwd_impl(L, y_true, y_true_stride, y_pred, y_pred_stride, n_pixels, use_weights, partials, nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int cvm_loss_fwd_total(const cvm_layout* L, const float* y_true, int y_true_stride, const float* y_pred,
+                                  int y_pred_stride, long long n_pixels, int use_weights, double* partials, float* out, void* ws,
+                                  size_t ws_bytes, void* stream) {
+    CVM_CHECK_ARG(out != nullptr, "out is NULL");
+    return loss_fwd_impl(L, y_true, y_true_stride, y_pred, y_pred_stride, n_pixels, use_weights, partials, out, ws, ws_bytes, stream);
+}
+
+namespace {
+// partials of n_ranks shards, summed in rank order (bit-reproducible whatever algorithm gathered them), then finalised
+__global__ void loss_finalize_gathered_kernel(const double* __restrict__ gathered, int n_ranks, double* __restrict__ partials,
+                                              float* __restrict__ out, const FinalizeParams fp) {
+    __shared__ double sum[CVM_NPART];
+    if (threadIdx.x < CVM_NPART) {
+        double t = 0.0;
+        for (int r = 0; r < n_ranks; ++r) t += gathered[(size_t)r * CVM_NPART + threadIdx.x];
+        sum[threadIdx.x] = t;
+        if (partials) partials[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && out) finalize_terms(sum, out, fp.n_fields, fp.f_post, fp.f_weight);
+}
+}  // namespace
+
+extern "C" int cvm_loss_finalize_gathered(const cvm_layout* L, const double* gathered, int n_ranks, double* partials, float* out,
+                                          void* stream) {
+    CVM_CHECK_ARG(L && gathered && (partials || out), "NULL pointer argument");
+    CVM_CHECK_ARG(n_ranks >= 1, "n_ranks < 1");
+    CVM_CHECK_ARG(L->n_fields >= 0 && L->n_fields <= CVM_MAX_FIELDS, "n_fields=%d", L->n_fields);
+    FinalizeParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.n_fields = L->n_fields;
+    for (int f = 0; f < L->n_fields; ++f) {
+        fp.f_post[f] = L->field_post[f];
+        fp.f_weight[f] = L->field_weight[f];
+    }
+    loss_finalize_gathered_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(gathered, n_ranks, partials, out, fp);
+    CVM_CHECK_LAUNCH("loss_finalize_gathered_kernel");
     return CVM_OK;
 }
 

@@ -65,6 +65,10 @@ def lib():
     L.cvm_loss_workspace_bytes.argtypes = [LP, i64]
     L.cvm_loss_fwd.restype = i32
     L.cvm_loss_fwd.argtypes = [LP, vp, i32, vp, i32, i64, i32, vp, vp, sz, vp]
+    L.cvm_loss_fwd_total.restype = i32
+    L.cvm_loss_fwd_total.argtypes = [LP, vp, i32, vp, i32, i64, i32, vp, vp, vp, sz, vp]
+    L.cvm_loss_finalize_gathered.restype = i32
+    L.cvm_loss_finalize_gathered.argtypes = [LP, vp, i32, vp, vp, vp]
     L.cvm_loss_finalize.restype = i32
     L.cvm_loss_finalize.argtypes = [LP, vp, vp, vp]
     L.cvm_loss_bwd.restype = i32
@@ -91,7 +95,7 @@ def lib():
 
 EXPORTS = [
     "cvm_last_error", "cvm_version", "cvm_prepare_objects", "cvm_render_gt", "cvm_render_prev_hm", "cvm_fill_heatmap_inplace", "cvm_loss_workspace_bytes",
-    "cvm_loss_fwd", "cvm_loss_finalize", "cvm_loss_bwd", "cvm_decode_topk_workspace_bytes", "cvm_decode_topk", "cvm_decode_topk_semseg", "cvm_decode_fallback_count",
+    "cvm_loss_fwd", "cvm_loss_fwd_total", "cvm_loss_finalize", "cvm_loss_finalize_gathered", "cvm_loss_bwd", "cvm_decode_topk_workspace_bytes", "cvm_decode_topk", "cvm_decode_topk_semseg", "cvm_decode_fallback_count",
     "cvm_decode_window9_workspace_bytes", "cvm_decode_window9", "cvm_semseg_argmax", "cvm_track_associate",
 ]
 

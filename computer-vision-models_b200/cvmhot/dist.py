@@ -33,10 +33,32 @@ def shard_range(n_items, rank, world):
 
 
 def allreduce_partials(partials, group=None):
-    """Sum the loss partials over all ranks (in place) — the one collective of the path."""
+    """Sum the loss partials over all ranks (in place) - the one collective of the path.  The ranks' vectors are gathered and
+    added in RANK ORDER, so every rank gets the same bits whatever algorithm the backend uses (an all-reduce may add in a
+    different order on different ranks or runs)."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
+        world = dist.get_world_size(group)
+        gathered = torch.empty((world,) + tuple(partials.shape), dtype=partials.dtype, device=partials.device)
+        dist.all_gather_into_tensor(gathered.view(-1), partials.contiguous().view(-1), group=group)
+        ordered_sum(gathered, out=partials)
     return partials
+
+
+def ordered_sum(gathered, out=None):
+    """Sum of gathered[r] over r in rank order (sequential adds: bit-reproducible).  On CUDA fp64 [n,16] inputs this is one
+    launch of cvm_loss_finalize_gathered; elsewhere a host-ordered loop."""
+    if out is None:
+        out = torch.empty_like(gathered[0])
+    if gathered.is_cuda and gathered.dtype == torch.float64 and gathered.dim() == 2 and gathered.shape[1] == 16:
+        from . import ops
+        from .layout import Layout
+        ops.loss_finalize_gathered(Layout(H=1, W=1, hm=1, nb_classes=1, Cp=1, Ct=2), gathered.contiguous(), partials=out, finalize=False)
+        return out
+    acc = gathered[0].clone()
+    for r in range(1, gathered.shape[0]):
+        acc = acc + gathered[r]
+    out.copy_(acc)
+    return out
 
 
 def finalize_partials_host(part, fields):

@@ -14,10 +14,21 @@ from cvmhot import _lib, ops
 from cvmhot.layout import layout_from_params
 
 
-def _allreduce(partials, group):
-    if group is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
-        torch.distributed.all_reduce(partials, op=torch.distributed.ReduceOp.SUM, group=group)
-    return partials
+def _distributed(group):
+    return group is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1
+
+
+def _loss_vector(layout, y_true, y_pred, use_weights, group):
+    """-> (out [total, focal, fields...], partials).  One launch on a single device (cvm_loss_fwd_total); with the batch
+    sharded over GPUs: partials, the ONE exchange of the path (an all-gather of 128 bytes per rank), then the rank-ordered
+    sum and the finalise step in one launch - bit-identical on every rank and to a single GPU working through the shards."""
+    if not _distributed(group):
+        return ops.loss_total(layout, y_true, y_pred, use_weights)
+    partials = ops.loss_partials(layout, y_true, y_pred, use_weights)
+    world = torch.distributed.get_world_size(group)
+    gathered = torch.empty((world, _lib.CVM_NPART), dtype=torch.float64, device=partials.device)
+    torch.distributed.all_gather_into_tensor(gathered.view(-1), partials, group=group)
+    return ops.loss_finalize_gathered(layout, gathered)
 
 
 class _LossFn(torch.autograd.Function):
@@ -25,8 +36,7 @@ class _LossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, y_pred, y_true, layout, group):
-        partials = _allreduce(ops.loss_partials(layout, y_true, y_pred, True), group)
-        out = ops.loss_finalize(layout, partials)
+        out, partials = _loss_vector(layout, y_true, y_pred, True, group)
         ctx.layout = layout
         ctx.save_for_backward(y_true, y_pred, partials)
         return out[0]
@@ -48,6 +58,7 @@ class CenternetLoss:
         self.params = params
         self.process_group = process_group
         self.obj_pos = [0, getattr(params, "HM_CHANNELS", 1)]
+        self._cache = {}
 
     # ---- helpers -------------------------------------------------------------------------------------------------------
     def _layout(self, y_true):
@@ -57,12 +68,28 @@ class CenternetLoss:
     def _f32(t):
         return t if t.dtype == torch.float32 else t.to(torch.float32)       # tf.cast(..., tf.float32), loss.py:134-135
 
+    def _vector(self, y_true, y_pred, use_weights):
+        """The finalised loss vector of (y_true, y_pred), computed ONCE per pair of tensors: the reference's
+        `metrics=[loss.class_loss, loss.r_offset_loss, loss.fullbox_loss, ...]` (train.py:62) calls every sub-term on the same
+        batch, and each term falls out of the same streaming pass.  An entry is reused only for the same storage, view
+        geometry and version counter (an in-place update or a new batch misses); it keeps its tensors alive, so their memory
+        cannot be handed to another tensor while the entry exists (one entry per weighting mode: at most the last batch)."""
+        L = self._layout(y_true)
+
+        def sig(t):
+            return (t.untyped_storage().data_ptr(), t.storage_offset(), tuple(t.shape[:-1]), t.stride(-2), t._version)
+
+        key = (sig(y_true), sig(y_pred))
+        hit = self._cache.get(bool(use_weights))
+        if hit is None or hit[0] != key:
+            out, _ = _loss_vector(L, y_true, y_pred, use_weights, self.process_group)
+            hit = self._cache[bool(use_weights)] = (key, out, L, y_true, y_pred)
+        return hit[1], hit[2]
+
     def terms(self, y_true, y_pred, use_weights=True):
         """All terms from ONE pass: dict(total, focal, <field names...>) of 0-d CUDA tensors.  y_true carries the weights plane."""
         y_true, y_pred = self._f32(y_true), self._f32(y_pred)
-        L = self._layout(y_true)
-        partials = _allreduce(ops.loss_partials(L, y_true, y_pred, use_weights), self.process_group)
-        out = ops.loss_finalize(L, partials)
+        out, L = self._vector(y_true, y_pred, use_weights)
         d = {"total": out[0], "obj_focal": out[1]}
         for i, name in enumerate(L.field_names()):
             d[name] = out[2 + i]
@@ -74,8 +101,7 @@ class CenternetLoss:
         L = self._layout(y_true)
         if y_true.shape[-1] < L.Cp:
             raise _lib.CvmError("y_true has fewer channels than the layout")
-        partials = _allreduce(ops.loss_partials(L, y_true, y_pred, False), self.process_group)
-        out = ops.loss_finalize(L, partials)
+        out, L = self._vector(y_true, y_pred, False)
         return out[2 + L.field_names().index(name)]
 
     # ---- reference API -------------------------------------------------------------------------------------------------
@@ -100,8 +126,7 @@ class CenternetLoss:
             st = y_true.stride(-2)
             if weights.data_ptr() != y_true.data_ptr() + 4 * (L.Ct - 1) or weights.stride(-1) != st:
                 raise _lib.CvmError("weights must be y_true[..., -1] of the full ground-truth tensor")
-        partials = _allreduce(ops.loss_partials(L, y_true, y_pred, use_w), self.process_group)
-        return ops.loss_finalize(L, partials)[1]
+        return self._vector(y_true, y_pred, use_w)[0][1]
 
     def class_loss(self, y_true, y_pred):
         return self._term(y_true, y_pred, "class")
@@ -139,5 +164,4 @@ class CenternetLoss:
         L.Cp, L.Ct = hm + f, hm + f + 1
         L.off_class = L.off_roff = L.off_box = L.off_track = -1
         L.fields = [("feat", hm, f, kinds[loss_type], _lib.POST_NONE, 1.0)]
-        partials = _allreduce(ops.loss_partials(L, yt, yp, False), self.process_group)
-        return ops.loss_finalize(L, partials)[2]
+        return _loss_vector(L, yt, yp, False, self.process_group)[0][2]

@@ -187,6 +187,27 @@ def loss_partials(layout: Layout, y_true, y_pred, use_weights=True, out=None):
     return out
 
 
+def loss_total(layout: Layout, y_true, y_pred, use_weights=True, partials=None, out=None):
+    """Single-device loss in ONE launch (cvm_loss_fwd_total): returns (out, partials) with out = float32 device vector
+    [total, focal, field_0, ...] and partials the fp64[16] vector (needed by loss_backward)."""
+    st_t = _pixel_strided(y_true, "y_true")
+    st_p = _pixel_strided(y_pred, "y_pred")
+    n = _n_pixels(y_true)
+    if _n_pixels(y_pred) != n:
+        raise _lib.CvmError("y_true and y_pred must cover the same pixels")
+    if partials is None:
+        partials = torch.empty(_lib.CVM_NPART, dtype=torch.float64, device=y_true.device)
+    if out is None:
+        out = torch.zeros(2 + _lib.CVM_MAX_FIELDS, dtype=torch.float32, device=y_true.device)
+    s = layout.c_struct()
+    nbytes = _lib.lib().cvm_loss_workspace_bytes(C.byref(s), n)
+    ws = _workspace(y_true.device, nbytes, "loss")
+    rc = _lib.lib().cvm_loss_fwd_total(C.byref(s), _ptr(y_true), st_t, _ptr(y_pred), st_p, n, int(bool(use_weights)),
+                                       _ptr(partials), _ptr(out), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "cvm_loss_fwd_total")
+    return out, partials
+
+
 def loss_finalize(layout: Layout, partials, out=None):
     """-> float32 device vector [total, focal, field_0, ...] (fields normalised, post-transformed, unweighted)."""
     _need_cuda(partials, "partials", torch.float64)
@@ -196,6 +217,27 @@ def loss_finalize(layout: Layout, partials, out=None):
     rc = _lib.lib().cvm_loss_finalize(C.byref(s), _ptr(partials), _ptr(out), _stream())
     _lib.check(rc, "cvm_loss_finalize")
     return out
+
+
+def loss_finalize_gathered(layout: Layout, gathered, partials=None, out=None, finalize=True):
+    """gathered [n_ranks,16] fp64 (every rank's partials) -> (out, partials): summed in rank order (bit-reproducible), finalised
+    (finalize=False: only the sum; out is None then)."""
+    _need_cuda(gathered, "gathered", torch.float64)
+    if gathered.dim() != 2 or gathered.shape[1] != _lib.CVM_NPART or not gathered.is_contiguous():
+        raise _lib.CvmError("gathered must be a contiguous [n_ranks, 16] float64 tensor")
+    if partials is None:
+        partials = torch.empty(_lib.CVM_NPART, dtype=torch.float64, device=gathered.device)
+    if out is None and finalize:
+        out = torch.zeros(2 + _lib.CVM_MAX_FIELDS, dtype=torch.float32, device=gathered.device)
+    s = layout.c_struct()
+    rc = _lib.lib().cvm_loss_finalize_gathered(C.byref(s), _ptr(gathered), int(gathered.shape[0]), _ptr(partials), _ptr(out), _stream())
+    _lib.check(rc, "cvm_loss_finalize_gathered")
+    return out, partials
+
+
+def decode_fallback_count():
+    """Images whose predicted decode threshold did not hold and that were recomputed by the slow exact path (monitoring)."""
+    return int(_lib.lib().cvm_decode_fallback_count())
 
 
 def loss_backward(layout: Layout, y_true, y_pred, partials, upstream=None, out=None):

@@ -137,6 +137,18 @@ size_t cvm_loss_workspace_bytes(const cvm_layout* L, long long n_pixels);
  * that is summed across GPUs before cvm_loss_finalize. */
 int cvm_loss_fwd(const cvm_layout* L, const float* y_true, int y_true_stride, const float* y_pred, int y_pred_stride,
                  long long n_pixels, int use_weights, double* partials, void* ws, size_t ws_bytes, void* stream);
+/* cvm_loss_fwd + cvm_loss_finalize in ONE launch, for callers that have nothing to sum across devices: the last block of
+ * the forward kernel reduces the block partials (fixed order: bit-reproducible) and applies the finalise step right
+ * away.  partials[CVM_NPART] is written as well (cvm_loss_bwd needs it); out as for cvm_loss_finalize. */
+int cvm_loss_fwd_total(const cvm_layout* L, const float* y_true, int y_true_stride, const float* y_pred, int y_pred_stride,
+                       long long n_pixels, int use_weights, double* partials, float* out, void* ws, size_t ws_bytes,
+                       void* stream);
+/* Data parallel: `gathered` [n_ranks][CVM_NPART] holds the partials of every rank (an all-gather of 128 bytes per rank).
+ * They are summed in RANK ORDER - the result is bit-identical on every rank and to one GPU processing the shards one after
+ * the other, whatever algorithm the collective used - written to `partials` (nullable; cvm_loss_bwd needs them) and
+ * finalised into `out` (nullable) in the same launch. */
+int cvm_loss_finalize_gathered(const cvm_layout* L, const double* gathered, int n_ranks, double* partials, float* out,
+                               void* stream);
 /* out[0] = total, out[1] = focal, out[2 + i] = field i (already normalised and post-transformed, unweighted). */
 int cvm_loss_finalize(const cvm_layout* L, const double* partials, float* out, void* stream);
 /* grad_pred [n_pixels, y_pred_stride-compatible: written with stride Cp] = upstream * d(total)/d(y_pred); needs the

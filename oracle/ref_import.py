@@ -15,15 +15,20 @@ MagicMock stubs, so that the NumPy/numba parts of the hot path run exactly as sh
   CentertrackerLoss       models/centertracker/loss.py:7-28   (same)
   MultitaskLoss           models/multitask/loss.py:13-47      (same; only calc_centernet is used)
 
-This only works in the build container (/root/reference does not exist on the GPU box); it is
-used by tests/golden/make_golden.py to generate the committed fixtures and by CPU tests that
-skip when the reference is not mounted. Nothing in the product path imports this file.
+The modules come from /root/reference in the build container and from its git-ignored copy oracle/_ref
+(oracle/make_ref.py) on the GPU box.  Used by tests/golden/make_golden.py to generate the committed
+fixtures, by the live-reference CPU tests and by bench.py's reference arm / cpu_baseline.  Nothing in the
+product path imports this file.
 """
 import os
 import sys
 from unittest.mock import MagicMock
 
+# the mounted reference in the build container; its copy under oracle/_ref (oracle/make_ref.py) on the GPU box
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = os.environ.get("CVM_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "models", "centernet")):
+    REFERENCE_ROOT = os.path.join(_HERE, "_ref")
 
 _STUBS = [
     "tensorflow", "tensorflow.keras", "tensorflow.keras.utils", "tensorflow.keras.losses",

@@ -118,28 +118,7 @@ def gen_to3(r, seed):
 
 
 # ---- loss: the UNMODIFIED reference loss files executed over oracle/tf_shim.py (TF ops on torch-CPU fp32) ----------------
-_POS_ATTRS = ("class_pos", "r_offset_pos", "fullbox_pos", "l_shape_pos", "radial_dist_pos", "orientation_pos",
-              "obj_dims_pos", "track_offset_pos")
-
-
-def ref_loss_object(r, nb, hm=1, track=False, l_shape=False, info3d=False):
-    """CenternetLoss / CentertrackerLoss of the reference (models/centernet/loss.py:6-29, centertracker/loss.py:7-14).
-    hm > 1 (Profile N): the reference hard-codes ONE heatmap channel (params.py:56, loss.py:12); the per-class-heatmap
-    layout is run through the very same reference lines by switching the class field off and moving the channel
-    positions the constructor pre-computed (instance attributes only, the class and its methods stay untouched)."""
-    P = (r["CentertrackerParams"] if track else r["CenternetParams"])(nb)
-    P.REGRESSION_FIELDS["l_shape"].active = l_shape
-    P.REGRESSION_FIELDS["3d_info"].active = info3d
-    if hm > 1:
-        P.REGRESSION_FIELDS["class"].active = False
-    loss = (r["CentertrackerLoss"] if track else r["CenternetLoss"])(P)
-    if hm > 1:
-        loss.obj_pos = [0, hm]
-        for a in _POS_ATTRS:
-            if hasattr(loss, a):
-                v = getattr(loss, a)
-                setattr(loss, a, [x + hm - 1 for x in v] if isinstance(v, list) else v + hm - 1)
-    return loss, P
+from oracle.ref_harness import ref_loss_object  # noqa: E402,F401
 
 
 def ref_loss_values(loss, y_true, y_pred):

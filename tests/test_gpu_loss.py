@@ -309,3 +309,38 @@ def test_cuda_multitask_vs_executed_reference(cuda, golden_dir):
     assert ml.semseg_offset["y_pred"] == list(z["semseg_offset_pred"]) and ml.depth_offset["y_pred"] == list(z["depth_offset_pred"])
     got = float(ml.calc_centernet(torch.from_numpy(yt).to(cuda), torch.from_numpy(yp).to(cuda)))
     assert got == pytest.approx(float(z["total"]), rel=RTOL)
+
+
+def test_metric_terms_share_one_pass(cuda, monkeypatch):
+    """The reference's metrics list (train.py:62) calls every sub-term on the same batch: the drop-in runs ONE fused pass for
+    all of them, a changed tensor (in place or a new one) triggers a new pass, and the single-device path is one launch
+    (cvm_loss_fwd_total) whose result equals partials + finalize."""
+    from cvmhot import ops
+    Lo = make_layout(24, 40, 5, "R")
+    yt, yp = _batch(Lo, 13, 2)
+    loss = _loss_cls(False)(_params(5, False, 24, 40))
+    yt_d, yp_d = torch.from_numpy(yt).to(cuda), torch.from_numpy(yp).to(cuda)
+    calls = []
+    real = ops.loss_total
+    monkeypatch.setattr(ops, "loss_total", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    vals = [float(f(yt_d, yp_d)) for f in (loss.obj_focal_loss, loss.class_loss, loss.r_offset_loss, loss.fullbox_loss)]
+    vals2 = [float(f(yt_d[..., :-1], yp_d)) for f in (loss.class_loss, loss.r_offset_loss, loss.fullbox_loss)]
+    assert len(calls) == 1 and vals[1:] == vals2
+    ref_total, ref_terms = loss_np.total_loss(Lo, yt, yp)
+    assert vals[1] == pytest.approx(ref_terms[1], rel=RTOL) and vals[3] == pytest.approx(ref_terms[3], rel=RTOL)
+    yp_d[0, 3, 3, Lo.off_box] += 5.0                      # in-place change: the cached vector must not be served
+    yp[0, 3, 3, Lo.off_box] += 5.0
+    pk = (yt[..., 0] == 1.0)
+    yp_d[torch.from_numpy(pk).to(cuda)] += 1.0
+    yp[pk] += 1.0
+    assert float(loss.fullbox_loss(yt_d, yp_d)) == pytest.approx(loss_np.total_loss(Lo, yt, yp)[1][3], rel=RTOL)
+    assert len(calls) == 2
+    yp2_d = yp_d.clone()                                  # a new tensor: new pass
+    loss.fullbox_loss(yt_d, yp2_d)
+    assert len(calls) == 3
+    # one launch == two launches
+    L = loss._layout(yt_d)
+    out1, part1 = real(L, yt_d, yp_d, True)
+    part2 = ops.loss_partials(L, yt_d, yp_d, True)
+    out2 = ops.loss_finalize(L, part2)
+    assert torch.equal(part1, part2) and torch.equal(out1[:2 + len(Lo.fields)], out2[:2 + len(Lo.fields)])
