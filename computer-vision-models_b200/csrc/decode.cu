@@ -53,7 +53,10 @@ constexpr int kGranBytes = 32768;  // target granule size
 constexpr int kUnroll = CVM_UNROLL;   // pixels per scanner lane and iteration
 constexpr int kQShift = 7;
 constexpr int kQCap = 1 << kQShift;   // records per queue (one queue per tester warp and segment parity)
-constexpr int kSlack = 1536;       // buffer entries beyond K before the (rare) fallback compaction
+#ifndef CVM_SLACK
+#define CVM_SLACK 1024
+#endif
+constexpr int kSlack = CVM_SLACK;       // buffer entries beyond K before the (rare) fallback compaction
 constexpr int kSegKeys = 512;      // keys a segment may publish without an exact select (the merge kernel selects anyway)
 constexpr int kScoreShift = 19;    // score histogram: bin = float bits >> 19 (sign 0, 8 exponent bits, 4 mantissa bits)
 constexpr int kScoreBins = 1 << (31 - kScoreShift);
@@ -185,6 +188,19 @@ size_t smem_bytes(int S, int gran_floats, int cap, int K) {
 // cycles per call next to a saturated memory system.)
 __device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 __device__ __forceinline__ void order_only() { asm volatile("" ::: "memory"); }
+
+// ring slot of load-order index x (x may be a little below zero for offsets that are never dereferenced)
+// (ring mode runs with 8 slots or 7, see plan_decode: a mask or a constant-divisor remainder.  A generic `x % S` here - it
+// is evaluated for every neighbour offset of every record - cost 16 % of the kernel.)
+// Only the instantiation for 64-byte pixels (CenterTracker: whole rows need the room of 7 slots) runs with a slot count that
+// is not a compile-time 8.
+template <int STRIDE, int HM>
+__device__ __forceinline__ int ring_slots(const DecodeParams& p) { return (STRIDE == 16 && HM == 10) ? p.S : kMaxSlots; }
+
+__device__ __forceinline__ int ring_slot(int S, int x) {
+    const unsigned u = (unsigned)(x + 7 * (1 << 20));
+    return S == kMaxSlots ? (x & (kMaxSlots - 1)) : (int)(u % 7u);
+}
 
 __device__ __forceinline__ unsigned ld_vol(const unsigned* p) { return *(volatile const unsigned*)p; }
 __device__ __forceinline__ int ld_vol(const int* p) { return *(volatile const int*)p; }
@@ -546,6 +562,18 @@ __device__ __forceinline__ float pixel_max(const float* px, int hm) {
     float m = __int_as_float(0xff800000);
     if (STRIDE == 0) {
         for (int c = 0; c < hm; ++c) m = fmaxf(m, px[c]);
+    } else if (STRIDE == 16 && HM == 10) {
+        // 64-byte pixels: lanes 0, 2, 4, 6 of a quarter warp would hit the same banks with the same 16-byte chunk; each lane
+        // pair starts at a different chunk instead (all four chunks are read: no bank conflicts, one load more)
+        const int r = ((threadIdx.x & 31) >> 1) & 3;
+        const float ninf = __int_as_float(0xff800000);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int cid = (r + j) & 3;
+            const float4 t = *reinterpret_cast<const float4*>(px + cid * 4);
+            const float half = fmaxf(t.x, t.y), full = fmaxf(half, fmaxf(t.z, t.w));
+            m = fmaxf(m, cid < 2 ? full : (cid == 2 ? half : ninf));   // channels 0-7 whole chunks, 8-9 half of chunk 2
+        }
     } else if (STRIDE % 4 == 0) {
 #pragma unroll
         for (int c = 0; c < HM; c += 4) {
@@ -608,11 +636,14 @@ __device__ __forceinline__ void q_push_marker(const DecodeParams& p, int par, un
 // Ring mode: has granule `ls` of the load order landed in its slot?  Its owner publishes that in landed_seq the moment it sees
 // it; before that, anybody may ask the slot's full barrier - but only once the slot's previous tenant (ls - kMaxSlots) is
 // known to have landed, because the parity test cannot tell phases two apart.
-__device__ __forceinline__ bool granule_landed(SharedHead* h, int ls) {
-    const int s = ls & (kMaxSlots - 1);
+__device__ __forceinline__ bool granule_landed(SharedHead* h, int S, int ls) {
+    const int s = ring_slot(S, ls);
     const int seq = ld_vol(&h->landed_seq[s]);
     if (seq >= ls + 1) return true;
-    if (seq >= ls + 1 - kMaxSlots) return mbar_try_wait(&h->full_bar[s], (uint32_t)((ls / kMaxSlots) & 1));
+    if (seq >= ls + 1 - S) {
+        const int turn = S == kMaxSlots ? ls >> 3 : (int)((unsigned)ls / 7u);
+        return mbar_try_wait(&h->full_bar[s], (uint32_t)(turn & 1));
+    }
     return false;
 }
 
@@ -741,16 +772,16 @@ __device__ __forceinline__ int prefilter_push(const DecodeParams& p, int slot, i
             rt = x < W - 1;
             rt_here = rt && pix < T - 1;   // (the right neighbour of a granule's last pixel is in the NEXT granule: the tester's)
             own = slot * G + pix * stride;
-            o_l = pix > 0 ? own - stride : ((slot - 1) & (kMaxSlots - 1)) * G + (T - 1) * stride;
+            o_l = pix > 0 ? own - stride : ring_slot(ring_slots<STRIDE, HM>(p), slot - 1) * G + (T - 1) * stride;
             o_r = own + stride;
             int o_up = pix - W, s_up = slot;
             while (o_up < 0) {
                 o_up += T;
-                s_up = (s_up - 1) & (kMaxSlots - 1);
+                s_up = ring_slot(ring_slots<STRIDE, HM>(p), s_up - 1);
             }
             o_um = s_up * G + o_up * stride;
-            o_ul = o_up > 0 ? o_um - stride : ((s_up - 1) & (kMaxSlots - 1)) * G + (T - 1) * stride;
-            o_ur = o_up < T - 1 ? o_um + stride : ((s_up + 1) & (kMaxSlots - 1)) * G;
+            o_ul = o_up > 0 ? o_um - stride : ring_slot(ring_slots<STRIDE, HM>(p), s_up - 1) * G + (T - 1) * stride;
+            o_ur = o_up < T - 1 ? o_um + stride : ring_slot(ring_slots<STRIDE, HM>(p), s_up + 1) * G;
             unsigned tb = ld_vol(&h->thr_bits[par]);
             tb = tb ? tb : 1u;
             thr_f = __uint_as_float(tb);
@@ -884,7 +915,7 @@ __device__ __forceinline__ void scanner_main(const DecodeParams& p, int w, long 
                 for (int k = 1; k <= p.hg && gi + k < p.gpi; ++k) {
                     int spins = 0;
                     STAT_T0();
-                    while (!__all_sync(kFull, granule_landed(h, ls + k))) {
+                    while (!__all_sync(kFull, granule_landed(h, nsw, ls + k))) {
                         __nanosleep(32);
                         SPIN_GUARD(spins, "wait for the lookahead granule");
                     }
@@ -1045,12 +1076,12 @@ __device__ __forceinline__ void test_records(const DecodeParams& p, const float*
         }
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            const int base = ((seg_ls0 + gr[r]) & (kMaxSlots - 1)) * p.gran_floats;
+            const int base = ring_slot(ring_slots<STRIDE, HM>(p), seg_ls0 + gr[r]) * p.gran_floats;
             off[r * 3 + 1] = base + orow[r] * stride;
             // left / right neighbour: the same granule unless the pixel sits at its edge
             off[r * 3 + 0] = orow[r] > 0 ? off[r * 3 + 1] - stride
-                                         : ((seg_ls0 + gr[r] - 1) & (kMaxSlots - 1)) * p.gran_floats + (T - 1) * stride;
-            off[r * 3 + 2] = orow[r] < T - 1 ? off[r * 3 + 1] + stride : ((seg_ls0 + gr[r] + 1) & (kMaxSlots - 1)) * p.gran_floats;
+                                         : ring_slot(ring_slots<STRIDE, HM>(p), seg_ls0 + gr[r] - 1) * p.gran_floats + (T - 1) * stride;
+            off[r * 3 + 2] = orow[r] < T - 1 ? off[r * 3 + 1] + stride : ring_slot(ring_slots<STRIDE, HM>(p), seg_ls0 + gr[r] + 1) * p.gran_floats;
         }
     } else {
 #pragma unroll
@@ -1162,13 +1193,13 @@ __device__ __forceinline__ void confirm_records(const DecodeParams& p, int seg_l
     STAT_LAP(17);
     float m = ninf;
     if (dn) {
-        const int o_dm = ((seg_ls0 + g_dn) & (kMaxSlots - 1)) * G + o_dn * stride + ch;
-        const int o_dl = o_dn > 0 ? o_dm - stride : ((seg_ls0 + g_dn - 1) & (kMaxSlots - 1)) * G + (T - 1) * stride + ch;
-        const int o_dr = o_dn < T - 1 ? o_dm + stride : ((seg_ls0 + g_dn + 1) & (kMaxSlots - 1)) * G + ch;
+        const int o_dm = ring_slot(ring_slots<STRIDE, HM>(p), seg_ls0 + g_dn) * G + o_dn * stride + ch;
+        const int o_dl = o_dn > 0 ? o_dm - stride : ring_slot(ring_slots<STRIDE, HM>(p), seg_ls0 + g_dn - 1) * G + (T - 1) * stride + ch;
+        const int o_dr = o_dn < T - 1 ? o_dm + stride : ring_slot(ring_slots<STRIDE, HM>(p), seg_ls0 + g_dn + 1) * G + ch;
         const float a0 = lf ? ring[o_dl] : ninf, a1 = ring[o_dm], a2 = rt ? ring[o_dr] : ninf;
         m = fmaxf(a0, fmaxf(a1, a2));
     }
-    if (right_later) m = fmaxf(m, ring[((seg_ls0 + g + 1) & (kMaxSlots - 1)) * G + ch]);
+    if (right_later) m = fmaxf(m, ring[ring_slot(ring_slots<STRIDE, HM>(p), seg_ls0 + g + 1) * G + ch]);
     // the threshold may have moved since the scan: only scores that still reach it (and are > 0) go in
     unsigned tb = ld_vol(&h->thr_bits[par]);
     tb = tb ? tb : 1u;
@@ -1694,32 +1725,40 @@ int plan_decode(const cvm_layout* L, int stride, int B, int K, int spare_sms, Pl
     // image rows (then a pixel's neighbourhood lies in the granules before / after its own: hg = 1), or, for rows wider than
     // a slot, 32-pixel multiples with hg = ceil((W + 1) / T) granules of history and lookahead (at most 3: the ring must
     // hold hg + 1 + hg granules plus the ones in flight).
-    const long long px_slot = (long long)(((size_t)kSmemBudget - fixed) / kMaxSlots / px_bytes);
     t->ring = 0;
     t->hg = 0;
+    t->S = kMaxSlots;
     int T = 0;
     if (HW < (1 << 24)) {
-        if (px_slot >= W) {
+        // whole rows: all slots, or - only in the kernel instantiation for 16-float pixels with 10 heatmap channels - one fewer
+        for (int S = kMaxSlots; S >= (stride == 16 && L->hm == 10 ? kMaxSlots - 1 : kMaxSlots) && !t->ring; --S) {
+            const long long px_slot = (long long)(((size_t)kSmemBudget - fixed) / S / px_bytes);
+            if (px_slot < W) continue;
             long long rows = px_slot / W;
             if (rows > L->H) rows = L->H;
             while (rows > 1 && rows * W * (long long)px_bytes > kGranBytes) --rows;   // keep granules <= 32 KB ...
             while (rows > 1 && (L->H + rows - 1) / rows * (long long)B < 4LL * cvm_num_sms()) --rows;   // ... and a few per CTA
+            while (rows > 1 && rows * W > kMaxT) --rows;
+            if (rows * W > kMaxT) continue;
             T = (int)(rows * W);
             t->ring = 1;
             t->hg = 1;
-        } else if (px_slot >= 32) {
-            const int T2 = (int)(px_slot / 32 * 32);
+            t->S = S;
+        }
+        const long long px_slot = (long long)(((size_t)kSmemBudget - fixed) / kMaxSlots / px_bytes);
+        if (!t->ring && px_slot >= 32) {
+            int T2 = (int)(px_slot / 32 * 32);
+            if (T2 > kMaxT) T2 = kMaxT;
             const int hg = (W + 1 + T2 - 1) / T2;
             if (hg <= 3) {
                 T = T2;
                 t->ring = 1;
                 t->hg = hg;
+                t->S = kMaxSlots;
             }
         }
     }
-    if (t->ring) {
-        t->S = kMaxSlots;
-    } else {
+    if (!t->ring) {
         // L2 mode: granules of <= 32 KB (a multiple of 32 pixels), one ring slot per scanner warp: all kScanWarps of them
         // when 32-pixel granules fit, fewer for very wide pixels
         T = (int)(kGranBytes / px_bytes / 32 * 32);
@@ -1903,6 +1942,19 @@ extern "C" int cvm_decode_topk(const cvm_layout* L, const float* y_pred, int pre
                                const cvm_roi* rois, float* scores, int32_t* cls, long long* flat, float* centers,
                                float* boxes, float* track, void* ws, size_t ws_bytes, void* stream) {
     return decode_impl(L, y_pred, pred_stride, B, K, rois, scores, cls, flat, centers, boxes, track, 0, 0, nullptr, ws, ws_bytes, stream);
+}
+
+// the tiling cvm_decode_topk would use: out[0..7] = pixels per granule, granules per image, ring slots, ring mode (1: 3x3
+// neighbours from shared memory, 0: from global memory), halo granules, grid size, shared memory bytes, candidate capacity
+extern "C" int cvm_decode_plan(const cvm_layout* L, int pred_stride, int B, int K, long long* out8) {
+    int rc = check_decode_args(L, pred_stride, B, K);
+    if (rc != CVM_OK) return rc;
+    Plan t;
+    rc = plan_decode(L, pred_stride, B > 0 ? B : 1, K, 0, &t);
+    if (rc != CVM_OK) return rc;
+    out8[0] = t.T; out8[1] = t.gpi; out8[2] = t.S; out8[3] = t.ring; out8[4] = t.hg; out8[5] = t.grid;
+    out8[6] = (long long)t.smem_scan; out8[7] = t.cap;
+    return CVM_OK;
 }
 
 extern "C" long long cvm_decode_fallback_count(void) {

@@ -175,6 +175,11 @@ int cvm_decode_topk_semseg(const cvm_layout* L, const float* y_pred, int pred_st
                            float* scores, int32_t* cls, long long* flat, float* centers, float* boxes, float* track,
                            int seg_off, int seg_n, unsigned char* seg_ids, void* ws, size_t ws_bytes, void* stream);
 
+/* The tiling cvm_decode_topk uses for a shape (introspection for tests and docs; no device work): out8 = pixels per granule,
+ * granules per image, ring slots, ring mode (1: the 3x3 neighbours are read from shared memory, 0: from global memory),
+ * halo granules, grid size, shared memory bytes, candidate buffer capacity. */
+int cvm_decode_plan(const cvm_layout* L, int pred_stride, int B, int K, long long* out8);
+
 /* Monitoring.  cvm_decode_topk predicts each image's K-th best score from the image before it (and, through the workspace,
  * from the previous call) so that only a few hundred pixels per image need the exact 3x3 test; the prediction is verified
  * per image and an image it does not hold for is recomputed exactly by a slower path.  Results never depend on it.  This
