@@ -39,6 +39,19 @@ int cvm_num_sms();
         }                                                                               \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is sticky per (device, kernel): set it when a call needs more than any call
+// before it on this device, not on every launch.  (A race between two host threads only repeats the call.)
+#define CVM_SMEM_ATTR_ONCE(kernel, bytes)                                                                     \
+    do {                                                                                                      \
+        static size_t done_[64] = {0};                                                                        \
+        int dev_ = 0;                                                                                         \
+        CVM_CHECK_CUDA(cudaGetDevice(&dev_));                                                                 \
+        if (dev_ < 0 || dev_ >= 64 || (size_t)(bytes) > done_[dev_]) {                                        \
+            CVM_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            if (dev_ >= 0 && dev_ < 64) done_[dev_] = (size_t)(bytes);                                        \
+        }                                                                                                     \
+    } while (0)
+
 static inline bool cvm_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- device: mbarrier + 1-D bulk async copy (TMA engine, SASS: UBLKCP / SYNCS) -----------------------------------------

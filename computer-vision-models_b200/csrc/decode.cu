@@ -1806,12 +1806,7 @@ int check_decode_args(const cvm_layout* L, int stride, int B, int K) {
 
 template <int STRIDE, int HM, bool SEG, bool BULK>
 int launch_scan_one(const DecodeParams& p, const Plan& t, cudaStream_t st) {
-    static bool configured = false;   // once per kernel instantiation, not on every call
-    if (!configured) {
-        CVM_CHECK_CUDA(cudaFuncSetAttribute(decode_scan_kernel<STRIDE, HM, SEG, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)kSmemBudget));
-        configured = true;
-    }
+    CVM_SMEM_ATTR_ONCE((decode_scan_kernel<STRIDE, HM, SEG, BULK>), kSmemBudget);
     decode_scan_kernel<STRIDE, HM, SEG, BULK><<<t.grid, kThreads, t.smem_scan, st>>>(p);
     CVM_CHECK_LAUNCH("decode_scan_kernel");
     return CVM_OK;
@@ -1916,12 +1911,7 @@ int decode_impl(const cvm_layout* L, const float* y_pred, int pred_stride, int B
     m.centers = centers;
     m.boxes = boxes;
     m.track = track;
-    static bool merge_configured = false;
-    if (!merge_configured) {
-        const size_t max_merge = ((size_t)kMergeCap + 3 * (size_t)kMaxK) * 8;
-        CVM_CHECK_CUDA(cudaFuncSetAttribute(decode_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_merge));
-        merge_configured = true;
-    }
+    CVM_SMEM_ATTR_ONCE(decode_merge_kernel, ((size_t)kMergeCap + 3 * (size_t)kMaxK) * 8);
     // (tried: programmatic dependent launch of the merge kernel, griddepcontrol.launch_dependents at the top of the scan:
     // 0.143 ms instead of 0.139 for the pair - the early-resident merge CTAs are in the way more than the launch gap costs)
     decode_merge_kernel<<<B, kMergeThreads, t.smem_merge, st>>>(m);

@@ -549,7 +549,7 @@ int launch_loss_fast(LossParams& p, cudaStream_t st, int* grid_out) {
     p.n_stages = n_stages;
     const size_t smem = (size_t)n_stages * stage_bytes;
     const int grid = loss_grid(p.n_spans, smem);
-    CVM_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_fast_kernel<HM, ST_T, ST_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CVM_SMEM_ATTR_ONCE((loss_fwd_fast_kernel<HM, ST_T, ST_P>), smem);
     loss_fwd_fast_kernel<HM, ST_T, ST_P><<<grid, kFastThreads + 32, smem, st>>>(p);
     CVM_CHECK_LAUNCH("loss_fwd_fast_kernel");
     *grid_out = grid;
@@ -643,7 +643,7 @@ int loss_fwd_impl(const cvm_layout* L, const float* y_true, int y_true_stride, c
 #undef CVM_LOSS_FAST
     if (grid == 0) {            // any other layout: runtime-parameterised kernel
         grid = loss_grid(p.n_spans, smem);
-        CVM_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CVM_SMEM_ATTR_ONCE((loss_fwd_kernel), smem);
         loss_fwd_kernel<<<grid, kThreads, smem, st>>>(p);
         CVM_CHECK_LAUNCH("loss_fwd_kernel");
     }
@@ -1097,7 +1097,7 @@ int launch_bwd_fast(BwdParams& bp, long long n_full_spans, cudaStream_t st) {
     p.n_stages = n_stages;
     const size_t smem = (size_t)n_stages * stage_bytes;
     const int grid = loss_grid(p.n_spans, smem);
-    CVM_CHECK_CUDA(cudaFuncSetAttribute(loss_bwd_fast_kernel<HM, ST_T, ST_P, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CVM_SMEM_ATTR_ONCE((loss_bwd_fast_kernel<HM, ST_T, ST_P, CP>), smem);
     loss_bwd_fast_kernel<HM, ST_T, ST_P, CP><<<grid, kBwdThreads + 32, smem, st>>>(bp);
     CVM_CHECK_LAUNCH("loss_bwd_fast_kernel");
     return CVM_OK;
@@ -1105,9 +1105,10 @@ int launch_bwd_fast(BwdParams& bp, long long n_full_spans, cudaStream_t st) {
 
 }  // namespace
 
-extern "C" int cvm_loss_bwd(const cvm_layout* L, const float* y_true, int y_true_stride, const float* y_pred,
-                            int y_pred_stride, long long n_pixels, const double* partials, const float* upstream,
-                            float* grad_pred, void* stream) {
+namespace {
+int loss_bwd_impl(const cvm_layout* L, const float* y_true, int y_true_stride, const float* y_pred, int y_pred_stride,
+                  long long n_pixels, const double* partials, const float* upstream, float* grad_pred, bool force_generic,
+                  void* stream) {
     int rc = check_layout_for_loss(L, y_true_stride, y_pred_stride);
     if (rc != CVM_OK) return rc;
     CVM_CHECK_ARG(y_true && y_pred && partials && grad_pred, "NULL pointer argument");
@@ -1153,7 +1154,6 @@ extern "C" int cvm_loss_bwd(const cvm_layout* L, const float* y_true, int y_true
     // fast path: compile-time layout, everything 16-byte aligned, alpha = 2 / beta = 4; it takes the full spans, the generic
     // kernel the ragged tail (or everything)
     long long done_pixels = 0;
-    const bool force_generic = getenv("CVM_LOSS_BWD_GENERIC") != nullptr;   // test knob: fast vs generic kernel
     if (p.use_bulk && bp.grad_bulk && p.a_is2 && p.b_is4 && !force_generic) {
         const long long n_full = n_pixels / kBwdThreads;
         BwdParams fb = bp;
@@ -1175,9 +1175,24 @@ extern "C" int cvm_loss_bwd(const cvm_layout* L, const float* y_true, int y_true
         p.use_bulk = cvm_aligned16(p.yt) && cvm_aligned16(p.yp);
         bp.grad_bulk = cvm_aligned16(bp.grad);
         const int grid = loss_grid(p.n_spans, smem);
-        CVM_CHECK_CUDA(cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CVM_SMEM_ATTR_ONCE((loss_bwd_kernel), smem);
         loss_bwd_kernel<<<grid, kThreads, smem, st>>>(bp);
         CVM_CHECK_LAUNCH("loss_bwd_kernel");
     }
     return CVM_OK;
+}
+}  // namespace
+
+extern "C" int cvm_loss_bwd(const cvm_layout* L, const float* y_true, int y_true_stride, const float* y_pred,
+                            int y_pred_stride, long long n_pixels, const double* partials, const float* upstream,
+                            float* grad_pred, void* stream) {
+    return loss_bwd_impl(L, y_true, y_true_stride, y_pred, y_pred_stride, n_pixels, partials, upstream, grad_pred, false, stream);
+}
+
+// the same gradient from the layout-generic kernel only (what every layout without a compile-time instantiation gets); the
+// tests compare the two on the BASELINE shapes
+extern "C" int cvm_loss_bwd_generic(const cvm_layout* L, const float* y_true, int y_true_stride, const float* y_pred,
+                                    int y_pred_stride, long long n_pixels, const double* partials, const float* upstream,
+                                    float* grad_pred, void* stream) {
+    return loss_bwd_impl(L, y_true, y_true_stride, y_pred, y_pred_stride, n_pixels, partials, upstream, grad_pred, true, stream);
 }

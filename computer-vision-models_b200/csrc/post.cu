@@ -389,7 +389,7 @@ extern "C" int cvm_track_associate(const float* centers, const float* track, con
     p.K = K;
     p.M = M;
     p.min_score = min_score;
-    if (smem > 48 * 1024) CVM_CHECK_CUDA(cudaFuncSetAttribute(track_associate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) CVM_SMEM_ATTR_ONCE((track_associate_kernel), smem);
     track_associate_kernel<<<B, 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     CVM_CHECK_LAUNCH("track_associate_kernel");
     return CVM_OK;

@@ -15,12 +15,23 @@
 // shared -> global) streams the chunk out while the SM's other CTA builds its chunk.  No store instruction
 // touches global memory on the fast path.  All gaussian math is fp64 like the reference's (scalar fp64 stored as fp32);
 // the separable factors exp(-ax), exp(-ay) are tabulated (per image / per chunk), see render_kernel.
+// (Tried in round 2: the per-chunk integer bookkeeping - ranges, first / last row, ignore-box test, a fifth of the kernel's
+// instructions because all 32 warps of an SM repeat it - done by ONE thread a chunk ahead and read from shared memory:
+// 0.173 ms instead of 0.163; the kernel is bound by the latency of its barrier-separated phases, and the lone thread
+// lengthens exactly that.)
 #include <stdlib.h>
 
 #include "common.cuh"
 
 namespace {
 
+// -DCVM_EXPERIMENT: CVM_RENDER_SKIP switches phases of the kernel off (tools/time_render.py ablations; results are wrong).
+// The shipped build has no such knob: RDBG() is a compile-time 0.
+#ifdef CVM_EXPERIMENT
+#define RDBG(bit) (p.dbg_skip & (bit))
+#else
+#define RDBG(bit) 0
+#endif
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxObjSmem = 64;   // objects are processed in batches of this many
@@ -294,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
                     loaded_base = base;
                 }
                 // ---- work units of this chunk ----
-                if (tid < n && !(p.dbg_skip & 32)) {
+                if (tid < n && !RDBG(32)) {
                     const ObjDerived& d = sobj[tid];
                     if (max(d.y0, ya) < min(d.y1, yb + 1) && d.x0 < d.x1) {
                         const int u = (d.x1 - d.x0 + 31) >> 5;
@@ -308,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
                 if (p.bulk && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous chunk has left the buffer
                 __syncthreads();   // ---- barrier C: the buffer is free ----
                 // ---- phase 1: pattern fill (heat = 0, weights = 1, regression targets = 0; processor.py:267-268) ----
-                if (tid < n_fill && !(p.dbg_skip & 4)) {
+                if (tid < n_fill && !RDBG(4)) {
                     const int n4 = (npx * Cout + 3) >> 2;   // the buffer is a whole number of float4s
                     float4* s4 = reinterpret_cast<float4*>(st);
                     for (int f = tid; f < n4; f += n_fill) s4[f] = fill_v;
@@ -321,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
             //      different objects overlap).  Items are dealt round-robin to the warps; order is irrelevant ----
             const int total = s_nunits[par];
             const bool overflow = total > kMaxUnits;   // absurdly many wide objects: whole-object items instead
-            const int n_items = (p.dbg_skip & 1) ? 0 : (overflow ? n : total);
+            const int n_items = RDBG(1) ? 0 : (overflow ? n : total);
             for (int it = warp; it < n_items; it += kWarps) {
                 const int u = overflow ? it : s_unit[it];
                 const ObjDerived& d = sobj[u & 255];
@@ -363,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
                 }
             }
             // centre scatter: regression targets and the class one-hot live in channels the splat never touches
-            if (scatter && tid < n && !(p.dbg_skip & 64)) {
+            if (scatter && tid < n && !RDBG(64)) {
                 const ObjDerived& d = sobj[tid];
                 const int qs = d.scy * W + d.scx;
                 if (d.scx >= 0 && qs >= q0 && qs < q1) {
@@ -389,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
 
         // ---- phase 3: ignore areas: weights = 0, input-px numbers used as mask indices (processor.py:318-323) ----
         bool ign_hit = n_ign > kMaxIgnSmem || (n_ign > 0 && n_batches == 0);   // (boxes beyond the cache / no barrier yet: take the slow way)
-        for (int i = 0; i < ((p.dbg_skip & 128) ? 0 : min(n_ign, kMaxIgnSmem)) && !ign_hit; ++i)
+        for (int i = 0; i < (RDBG(128) ? 0 : min(n_ign, kMaxIgnSmem)) && !ign_hit; ++i)
             ign_hit = s_ign[i][0] < s_ign[i][1] && max(s_ign[i][2], ya) < min(s_ign[i][3], yb + 1);
         if (ign_hit) {   // uniform: few chunks meet an ignore box
             __syncthreads();   // all splats are in (and s_ign is visible when the image had no objects)
@@ -415,10 +426,10 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
 
         // ---- stream the chunk out ----
         if (p.bulk) {
-            if (!(p.dbg_skip & 16)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk engine
+            if (!RDBG(16)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk engine
             __syncthreads();   // ---- barrier B: the chunk is complete ----
             // the buffer is rebuilt only after barrier C of the next iteration (meanwhile the SM's other CTA builds its chunk)
-            if (tid == 0 && !(p.dbg_skip & 2)) bulk_s2g(p.out + ((size_t)img * HW + q0) * Cout, st, (uint32_t)(npx * Cout * 4));
+            if (tid == 0 && !RDBG(2)) bulk_s2g(p.out + ((size_t)img * HW + q0) * Cout, st, (uint32_t)(npx * Cout * 4));
         } else {
             __syncthreads();
             float* const dst = p.out + ((size_t)img * HW + q0) * Cout;
@@ -453,7 +464,10 @@ int launch_render(const RenderParams& p0, int B, cudaStream_t st) {
     RenderParams p = p0;
     p.HW = p.H * p.W;
     int P = (kChunkBytes / (p.Cout * 4)) & ~3;
-    if (P > 4096) P = 4096;   // keeps the (object, row) items of a chunk short for narrow outputs (prev-frame heatmap)
+    // narrow outputs: 4096-pixel chunks keep the (object, row) items of a chunk short; the one-channel previous-frame
+    // heatmap takes 64 KB chunks (0.121 -> 0.097 ms for the 512 images of BASELINE configs[3])
+    const int p_cap = p.Cout == 1 ? 16384 : 4096;
+    if (P > p_cap) P = p_cap;
     if (P > ((p.HW + 3) & ~3)) P = (p.HW + 3) & ~3;
     CVM_CHECK_ARG(P >= 4 && p.Cout <= kThreads, "render: %d output channels do not fit the staging buffer", p.Cout);
     p.P = P;
@@ -464,10 +478,12 @@ int launch_render(const RenderParams& p0, int B, cudaStream_t st) {
     // P % 4 == 0, the partial last chunk of an image then ends on a granule too)
     p.bulk = cvm_aligned16(p.out) && (((long long)p.HW * p.Cout) % 4 == 0);
     p.vec = p.bulk;
+#ifdef CVM_EXPERIMENT
     if (const char* e = getenv("CVM_RENDER_SKIP")) p.dbg_skip = atoi(e);
-    if (p.dbg_skip & 8) p.bulk = 0;   // experiment: plain stores instead of bulk copies
+    if RDBG(8) p.bulk = 0;   // experiment: plain stores instead of bulk copies
+#endif
     const size_t smem = (size_t)kChunkBytes;
-    CVM_CHECK_CUDA(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CVM_SMEM_ATTR_ONCE((render_kernel), smem);
     long long grid = 2LL * cvm_num_sms();
     if (grid > p.n_chunks) grid = p.n_chunks;
     render_kernel<<<(unsigned)grid, kThreads, smem, st>>>(p);

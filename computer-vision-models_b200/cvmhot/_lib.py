@@ -73,6 +73,8 @@ def lib():
     L.cvm_loss_finalize.argtypes = [LP, vp, vp, vp]
     L.cvm_loss_bwd.restype = i32
     L.cvm_loss_bwd.argtypes = [LP, vp, i32, vp, i32, i64, vp, vp, vp, vp]
+    L.cvm_loss_bwd_generic.restype = i32
+    L.cvm_loss_bwd_generic.argtypes = [LP, vp, i32, vp, i32, i64, vp, vp, vp, vp]
     L.cvm_decode_topk_workspace_bytes.restype = sz
     L.cvm_decode_topk_workspace_bytes.argtypes = [LP, i32, i32, i32]
     L.cvm_decode_topk.restype = i32
@@ -97,7 +99,7 @@ def lib():
 
 EXPORTS = [
     "cvm_last_error", "cvm_version", "cvm_prepare_objects", "cvm_render_gt", "cvm_render_prev_hm", "cvm_fill_heatmap_inplace", "cvm_loss_workspace_bytes",
-    "cvm_loss_fwd", "cvm_loss_fwd_total", "cvm_loss_finalize", "cvm_loss_finalize_gathered", "cvm_loss_bwd", "cvm_decode_topk_workspace_bytes", "cvm_decode_topk", "cvm_decode_topk_semseg", "cvm_decode_fallback_count", "cvm_decode_plan",
+    "cvm_loss_fwd", "cvm_loss_fwd_total", "cvm_loss_finalize", "cvm_loss_finalize_gathered", "cvm_loss_bwd", "cvm_loss_bwd_generic", "cvm_decode_topk_workspace_bytes", "cvm_decode_topk", "cvm_decode_topk_semseg", "cvm_decode_fallback_count", "cvm_decode_plan",
     "cvm_decode_window9_workspace_bytes", "cvm_decode_window9", "cvm_semseg_argmax", "cvm_track_associate",
 ]
 

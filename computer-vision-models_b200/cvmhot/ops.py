@@ -240,8 +240,9 @@ def decode_fallback_count():
     return int(_lib.lib().cvm_decode_fallback_count())
 
 
-def loss_backward(layout: Layout, y_true, y_pred, partials, upstream=None, out=None):
-    """grad wrt y_pred[..., :Cp] as a contiguous [n_pixels, Cp] tensor; `partials` must be the globally reduced vector."""
+def loss_backward(layout: Layout, y_true, y_pred, partials, upstream=None, out=None, generic=False):
+    """grad wrt y_pred[..., :Cp] as a contiguous [n_pixels, Cp] tensor; `partials` must be the globally reduced vector.
+    generic=True: the layout-generic kernel only (cvm_loss_bwd_generic; tests compare it with the compile-time layouts)."""
     st_t = _pixel_strided(y_true, "y_true")
     st_p = _pixel_strided(y_pred, "y_pred")
     n = _n_pixels(y_true)
@@ -250,8 +251,8 @@ def loss_backward(layout: Layout, y_true, y_pred, partials, upstream=None, out=N
     if upstream is not None:
         _need_cuda(upstream, "upstream", torch.float32)
     s = layout.c_struct()
-    rc = _lib.lib().cvm_loss_bwd(C.byref(s), _ptr(y_true), st_t, _ptr(y_pred), st_p, n, _ptr(partials), _ptr(upstream),
-                                 _ptr(out), _stream())
+    fn = _lib.lib().cvm_loss_bwd_generic if generic else _lib.lib().cvm_loss_bwd
+    rc = fn(C.byref(s), _ptr(y_true), st_t, _ptr(y_pred), st_p, n, _ptr(partials), _ptr(upstream), _ptr(out), _stream())
     _lib.check(rc, "cvm_loss_bwd")
     return out
 

@@ -157,6 +157,11 @@ int cvm_loss_bwd(const cvm_layout* L, const float* y_true, int y_true_stride, co
                  long long n_pixels, const double* partials, const float* upstream /* device scalar or NULL (=1) */,
                  float* grad_pred, void* stream);
 
+/* cvm_loss_bwd through the layout-generic kernel only (the path of every layout without a compile-time instantiation); same
+ * result within rounding - exposed so that callers / tests can compare the two. */
+int cvm_loss_bwd_generic(const cvm_layout* L, const float* y_true, int y_true_stride, const float* y_pred, int y_pred_stride,
+                         long long n_pixels, const double* partials, const float* upstream, float* grad_pred, void* stream);
+
 /* ---- decode -------------------------------------------------------------------------------------------------- */
 size_t cvm_decode_topk_workspace_bytes(const cvm_layout* L, int pred_stride, int B, int K);   /* 0 = unsupported shape */
 /* y_pred [B,H,W,pred_stride] (pred_stride >= Cp).  Outputs (device): scores[B,K] f32, cls[B,K] i32,

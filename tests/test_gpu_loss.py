@@ -208,9 +208,7 @@ def test_backward_full_size_fast_equals_generic(cuda, monkeypatch):
     yp_d[..., K:] = torch.rand((B, H, W, Lo.Cp - K), device=cuda, generator=g) * 40
     part = ops.loss_partials(L, yt_d, yp_d, True).clone()
     fast = ops.loss_backward(L, yt_d, yp_d, part).clone()
-    monkeypatch.setenv("CVM_LOSS_BWD_GENERIC", "1")
-    generic = ops.loss_backward(L, yt_d, yp_d, part).clone()
-    monkeypatch.delenv("CVM_LOSS_BWD_GENERIC")
+    generic = ops.loss_backward(L, yt_d, yp_d, part, generic=True).clone()
     assert torch.isfinite(fast).all()
     scale = float(generic.abs().max())
     assert torch.allclose(fast, generic, rtol=1e-5, atol=scale * 1e-7)
