@@ -329,6 +329,7 @@ def run_ours(args):
     cfg = CONFIGS[args.config]
     Hm, Wm = cfg["H"], cfg["W"]
     B = args.batch or cfg["batch"]
+    ops.set_decode_spare_sms(args.spare_sms if args.spare_sms >= 0 else (2 if world > 1 and args.config == 2 else 0))
 
     p = (CentertrackerParams if cfg["track"] else CenternetParams)(NB_CLASSES, per_class_heatmap=True)
     p.INPUT_HEIGHT, p.INPUT_WIDTH = Hm * 2, Wm * 2
@@ -612,6 +613,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5], help="BASELINE.json configs[config-1]")
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
     ap.add_argument("--chunks", type=int, default=4, help="e2e leg: H2D chunks per step")
+    ap.add_argument("--spare-sms", type=int, default=-1, help="SMs the decode leaves to the collective (default: 2 when N > 1)")
     ap.add_argument("--check", action="store_true", help="N > 1: compare the sharded loss partials with one GPU, bit for bit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -1706,6 +1706,11 @@ __global__ void __launch_bounds__(kMergeThreads) decode_merge_kernel(const Merge
 
 
 
+// SMs the scan kernel leaves free (cvm_decode_set_spare_sms): a data-parallel caller that issues its small collective just
+// before the decode sets 1, so that the collective's kernel finds an SM at once instead of waiting for a persistent scan CTA
+// to retire (every scan CTA takes a whole SM's shared memory)
+int g_spare_sms = 0;
+
 struct Plan {
     int T, gpi, S, ring, hg, gran_floats, cap, compact_at, grid, max_segs, seg_keys;
     long long n_gran;
@@ -1828,7 +1833,7 @@ int decode_impl(const cvm_layout* L, const float* y_pred, int pred_stride, int B
     if (seg_out) CVM_CHECK_ARG(seg_n >= 1 && seg_n <= 256 && seg_off >= 0 && seg_off + seg_n <= pred_stride, "bad semseg slice");
     if (B == 0) return CVM_OK;
     Plan t;
-    rc = plan_decode(L, pred_stride, B, K, 0, &t);
+    rc = plan_decode(L, pred_stride, B, K, g_spare_sms, &t);
     CVM_CHECK_ARG(rc == CVM_OK, "no tiling for H=%d W=%d hm=%d stride=%d K=%d", L->H, L->W, L->hm, pred_stride, K);
     if (ws_bytes < t.ws_total) {
         cvm_set_error("workspace too small: %zu < %zu", ws_bytes, t.ws_total);
@@ -1924,7 +1929,7 @@ int decode_impl(const cvm_layout* L, const float* y_pred, int pred_stride, int B
 extern "C" size_t cvm_decode_topk_workspace_bytes(const cvm_layout* L, int pred_stride, int B, int K) {
     if (check_decode_args(L, pred_stride, B, K) != CVM_OK) return 0;
     Plan t;
-    if (plan_decode(L, pred_stride, B > 0 ? B : 1, K, 0, &t) != CVM_OK) return 0;
+    if (plan_decode(L, pred_stride, B > 0 ? B : 1, K, g_spare_sms, &t) != CVM_OK) return 0;
     return t.ws_total;
 }
 
@@ -1940,10 +1945,16 @@ extern "C" int cvm_decode_plan(const cvm_layout* L, int pred_stride, int B, int 
     int rc = check_decode_args(L, pred_stride, B, K);
     if (rc != CVM_OK) return rc;
     Plan t;
-    rc = plan_decode(L, pred_stride, B > 0 ? B : 1, K, 0, &t);
+    rc = plan_decode(L, pred_stride, B > 0 ? B : 1, K, g_spare_sms, &t);
     if (rc != CVM_OK) return rc;
     out8[0] = t.T; out8[1] = t.gpi; out8[2] = t.S; out8[3] = t.ring; out8[4] = t.hg; out8[5] = t.grid;
     out8[6] = (long long)t.smem_scan; out8[7] = t.cap;
+    return CVM_OK;
+}
+
+extern "C" int cvm_decode_set_spare_sms(int n) {
+    CVM_CHECK_ARG(n >= 0 && n < 64, "spare SMs must be in [0, 64)");
+    g_spare_sms = n;
     return CVM_OK;
 }
 

@@ -125,11 +125,22 @@ __device__ __forceinline__ void last_block_reduce(const LossParams& p) {
     if (!s_last) return;
     __threadfence();
     const int n_blocks = (int)gridDim.x;
-    const volatile double* bp = p.block_partials;
+    const double* bp = p.block_partials;
     for (int t = threadIdx.x; t < 16 * CVM_NPART; t += NT) {
         const int k = t % CVM_NPART, g = t / CVM_NPART;
         double r = 0.0;
-        for (int b = g; b < n_blocks; b += 16) r += bp[(size_t)b * CVM_NPART + k];
+        // (L2 loads, eight in flight at a time; the additions stay in block order)
+        for (int b0 = g; b0 < n_blocks; b0 += 16 * 8) {
+            double v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int b = b0 + 16 * j;
+                v[j] = b < n_blocks ? __ldcg(bp + (size_t)b * CVM_NPART + k) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (b0 + 16 * j < n_blocks) r += v[j];
+        }
         sh[g][k] = r;
     }
     __syncthreads();

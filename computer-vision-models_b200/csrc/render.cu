@@ -36,9 +36,15 @@ constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxObjSmem = 64;   // objects are processed in batches of this many
 constexpr int kMaxIgnSmem = 16;     // ignore boxes cached in shared memory per image (more are read from global)
-constexpr int kChunkBytes = 86016;   // staging buffer per CTA (two CTAs per SM: one builds while the other's chunk streams out)
+#ifndef CVM_RENDER_CHUNK
+#define CVM_RENDER_CHUNK 81920
+#endif
+#ifndef CVM_RENDER_COLTAB
+#define CVM_RENDER_COLTAB 1536   /* the 32 objects of BASELINE configs[1] need ~1350 column entries; 80 KB chunks make room: 0.1606 -> 0.1571 ms */
+#endif
+constexpr int kChunkBytes = CVM_RENDER_CHUNK;   // staging buffer per CTA (two CTAs per SM: one builds while the other's chunk streams out)
 constexpr int kMaxUnits = 512;       // (object, 32-column segment) work units per chunk and object batch
-constexpr int kColTab = 1024;        // entries of the per-image column-factor table (objects that do not fit use exp)
+constexpr int kColTab = CVM_RENDER_COLTAB;        // entries of the per-image column-factor table (objects that do not fit use exp)
 constexpr int kRowTab = 1024;        // entries of the per-image row-factor table
 
 struct RenderParams {

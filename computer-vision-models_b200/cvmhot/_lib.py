@@ -81,6 +81,8 @@ def lib():
     L.cvm_decode_topk.argtypes = [LP, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.cvm_decode_topk_semseg.restype = i32
     L.cvm_decode_topk_semseg.argtypes = [LP, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, sz, vp]
+    L.cvm_decode_set_spare_sms.restype = i32
+    L.cvm_decode_set_spare_sms.argtypes = [i32]
     L.cvm_decode_plan.restype = i32
     L.cvm_decode_plan.argtypes = [LP, i32, i32, i32, vp]
     L.cvm_decode_fallback_count.restype = i64
@@ -99,7 +101,7 @@ def lib():
 
 EXPORTS = [
     "cvm_last_error", "cvm_version", "cvm_prepare_objects", "cvm_render_gt", "cvm_render_prev_hm", "cvm_fill_heatmap_inplace", "cvm_loss_workspace_bytes",
-    "cvm_loss_fwd", "cvm_loss_fwd_total", "cvm_loss_finalize", "cvm_loss_finalize_gathered", "cvm_loss_bwd", "cvm_loss_bwd_generic", "cvm_decode_topk_workspace_bytes", "cvm_decode_topk", "cvm_decode_topk_semseg", "cvm_decode_fallback_count", "cvm_decode_plan",
+    "cvm_loss_fwd", "cvm_loss_fwd_total", "cvm_loss_finalize", "cvm_loss_finalize_gathered", "cvm_loss_bwd", "cvm_loss_bwd_generic", "cvm_decode_topk_workspace_bytes", "cvm_decode_topk", "cvm_decode_topk_semseg", "cvm_decode_fallback_count", "cvm_decode_plan", "cvm_decode_set_spare_sms",
     "cvm_decode_window9_workspace_bytes", "cvm_decode_window9", "cvm_semseg_argmax", "cvm_track_associate",
 ]
 

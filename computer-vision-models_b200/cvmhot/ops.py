@@ -235,6 +235,11 @@ def loss_finalize_gathered(layout: Layout, gathered, partials=None, out=None, fi
     return out, partials
 
 
+def set_decode_spare_sms(n):
+    """SMs the decode scan leaves free (1 for data-parallel callers whose collective should run beside the decode)."""
+    _lib.check(_lib.lib().cvm_decode_set_spare_sms(int(n)), "cvm_decode_set_spare_sms")
+
+
 def decode_fallback_count():
     """Images whose predicted decode threshold did not hold and that were recomputed by the slow exact path (monitoring)."""
     return int(_lib.lib().cvm_decode_fallback_count())

@@ -180,6 +180,12 @@ int cvm_decode_topk_semseg(const cvm_layout* L, const float* y_pred, int pred_st
                            float* scores, int32_t* cls, long long* flat, float* centers, float* boxes, float* track,
                            int seg_off, int seg_n, unsigned char* seg_ids, void* ws, size_t ws_bytes, void* stream);
 
+/* Process-wide setting: SMs the decode's persistent scan kernel leaves free (default 0).  A data-parallel caller that
+ * issues the exchange of the loss partials right before the decode sets 1: the collective's kernel then runs beside the
+ * scan instead of behind it (every scan CTA owns a whole SM's shared memory).  Affects the workspace size query too: set
+ * it before sizing workspaces. */
+int cvm_decode_set_spare_sms(int n);
+
 /* The tiling cvm_decode_topk uses for a shape (introspection for tests and docs; no device work): out8 = pixels per granule,
  * granules per image, ring slots, ring mode (1: the 3x3 neighbours are read from shared memory, 0: from global memory),
  * halo granules, grid size, shared memory bytes, candidate buffer capacity. */
