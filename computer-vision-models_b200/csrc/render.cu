@@ -63,6 +63,8 @@ struct RenderParams {
     int per_class;     // 1: heat plane = obj.cls (Profile N); 0: plane 0 (reference as shipped)
     int force_explicit;
     int off_class, off_roff, off_box, off_track;
+    const float* extra;  // per-object extra regression targets [n_obj][extra_stride] (l_shape / 3d_info, processor.py:296-299) or NULL
+    int extra_stride, extra_off, extra_n;   // written to channels [extra_off, extra_off + extra_n) of the centre pixel
     int bulk;          // chunks are 16-byte aligned in global memory: stream them out with bulk async copies
     int vec;           // chunks are 16-byte aligned: the plain-store path may use 128-bit stores
     int dbg_skip;      // experiment knob (CVM_RENDER_SKIP): 1 = no splat, 2 = no store, 4 = no fill
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
         fill_v.z = ((r + 2) % Cout == wch) ? 1.f : 0.f;
         fill_v.w = ((r + 3) % Cout == wch) ? 1.f : 0.f;
     }
-    const bool scatter = p.off_class >= 0 || p.off_roff >= 0 || p.off_box >= 0 || p.off_track >= 0;
+    const bool scatter = p.off_class >= 0 || p.off_roff >= 0 || p.off_box >= 0 || p.off_track >= 0 || p.extra_n > 0;
     int loaded_img = -1;         // image whose per-image state (ranges, ignore boxes, first object batch) is loaded
     int loaded_base = -1;        // first object of the batch in sobj
     int o_begin = 0, o_end = 0, i_begin = 0, n_ign = 0, n_batches = 0;
@@ -399,6 +401,10 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
                             px[p.off_track] = d.tx;
                             px[p.off_track + 1] = d.ty;
                         }
+                        if (p.extra_n > 0) {   // l_shape (7) / 3d_info (5) targets, computed on the host (processor.py:69-115,296-299)
+                            const float* e = p.extra + (size_t)(base + tid) * p.extra_stride;
+                            for (int k = 0; k < p.extra_n; ++k) px[p.extra_off + k] = e[k];
+                        }
                     }
                 }
             }
@@ -501,7 +507,15 @@ int launch_render(const RenderParams& p0, int B, cudaStream_t st) {
 
 extern "C" int cvm_render_gt(const cvm_layout* L, const cvm_obj* objs, const int32_t* obj_offsets, const cvm_box* ignore,
                              const int32_t* ign_offsets, int B, float* y_true, void* stream) {
+    return cvm_render_gt_extra(L, objs, obj_offsets, ignore, ign_offsets, B, nullptr, 0, 0, 0, y_true, stream);
+}
+
+extern "C" int cvm_render_gt_extra(const cvm_layout* L, const cvm_obj* objs, const int32_t* obj_offsets, const cvm_box* ignore,
+                                   const int32_t* ign_offsets, int B, const float* extra, int extra_stride, int extra_off,
+                                   int extra_n, float* y_true, void* stream) {
     CVM_CHECK_ARG(L && obj_offsets && y_true, "NULL pointer argument");
+    CVM_CHECK_ARG(extra_n == 0 || (extra && extra_n > 0 && extra_stride >= extra_n && extra_off >= L->hm && extra_off + extra_n <= L->Cp),
+                  "extra targets [%d, %d) must lie inside the regression channels [hm, Cp)", extra_off, extra_off + extra_n);
     CVM_CHECK_ARG(B >= 0 && L->H > 0 && L->W > 0, "bad shape");
     CVM_CHECK_ARG(L->hm >= 1 && L->hm <= 64 && L->Ct == L->Cp + 1 && L->Cp >= L->hm, "bad channel layout");
     CVM_CHECK_ARG((ignore == nullptr) == (ign_offsets == nullptr), "ignore and ign_offsets must both be given or both NULL");
@@ -523,6 +537,10 @@ extern "C" int cvm_render_gt(const cvm_layout* L, const cvm_obj* objs, const int
     p.off_roff = L->off_roff;
     p.off_box = L->off_box;
     p.off_track = L->off_track;
+    p.extra = extra_n > 0 ? extra : nullptr;
+    p.extra_stride = extra_stride;
+    p.extra_off = extra_off;
+    p.extra_n = extra_n;
     p.R = L->R;
     p.alpha = L->alpha;
     return launch_render(p, B, reinterpret_cast<cudaStream_t>(stream));

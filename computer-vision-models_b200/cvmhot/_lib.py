@@ -57,6 +57,8 @@ def lib():
     L.cvm_prepare_objects.argtypes = [vp, vp, vp, vp, i32, f64, f64, f64, vp, vp, vp, vp, vp]
     L.cvm_render_gt.restype = i32
     L.cvm_render_gt.argtypes = [LP, vp, vp, vp, vp, i32, vp, vp]
+    L.cvm_render_gt_extra.restype = i32
+    L.cvm_render_gt_extra.argtypes = [LP, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, vp]
     L.cvm_render_prev_hm.restype = i32
     L.cvm_render_prev_hm.argtypes = [LP, vp, vp, i32, vp, vp]
     L.cvm_fill_heatmap_inplace.restype = i32
@@ -100,7 +102,7 @@ def lib():
 
 
 EXPORTS = [
-    "cvm_last_error", "cvm_version", "cvm_prepare_objects", "cvm_render_gt", "cvm_render_prev_hm", "cvm_fill_heatmap_inplace", "cvm_loss_workspace_bytes",
+    "cvm_last_error", "cvm_version", "cvm_prepare_objects", "cvm_render_gt", "cvm_render_gt_extra", "cvm_render_prev_hm", "cvm_fill_heatmap_inplace", "cvm_loss_workspace_bytes",
     "cvm_loss_fwd", "cvm_loss_fwd_total", "cvm_loss_finalize", "cvm_loss_finalize_gathered", "cvm_loss_bwd", "cvm_loss_bwd_generic", "cvm_decode_topk_workspace_bytes", "cvm_decode_topk", "cvm_decode_topk_semseg", "cvm_decode_fallback_count", "cvm_decode_plan", "cvm_decode_set_spare_sms",
     "cvm_decode_window9_workspace_bytes", "cvm_decode_window9", "cvm_semseg_argmax", "cvm_track_associate",
 ]

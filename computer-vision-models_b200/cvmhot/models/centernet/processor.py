@@ -72,8 +72,6 @@ class ProcessImages(IPreProcessor):
         self.start_augmentation = start_augmentation
         self.show_debug_img = show_debug_img
         self.device = torch.device(device) if device is not None else torch.device("cuda")
-        if params.REGRESSION_FIELDS["l_shape"].active or params.REGRESSION_FIELDS["3d_info"].active:
-            raise NotImplementedError("render of l_shape / 3d_info targets is not part of the 2D heatmap path")
 
     # -- host-side box bookkeeping, same rules as the reference ---------------------------------------------------------
     def clip_to_img(self, bbox, min_x, min_y, max_x, max_y):
@@ -84,27 +82,82 @@ class ProcessImages(IPreProcessor):
         return [x0, y0, x1 - x0, y1 - y0]
 
     def calc_img_data(self, box2d, box3d, mask_width, mask_height):
-        """Centre pixel and sub-pixel offset of a box (reference processor.py:58-67); the device does the same math."""
-        if box3d is not None:
-            raise NotImplementedError("l_shape targets are outside the 2D heatmap path")
-        x, y, w, h = np.asarray(box2d, dtype=np.float64) / float(self.params.R)
+        """Centre pixel, sub-pixel offset and - from the 8 projected corners of the 3D box - the L-shape targets of an object
+        (reference processor.py:58-115): returns (center, loc_off, valid_l_shape, [bottom_left_off, bottom_center_off,
+        bottom_right_off, center_height]).  The device repeats the centre math; the L-shape is host math on 8 points."""
+        R = float(self.params.R)
+        x, y, w, h = np.asarray(box2d, dtype=np.float64) / R
         cxf, cyf = x + float(w) / 2.0, y + float(h) / 2.0
         cx = max(0, min(mask_width - 1, int(cxf)))
         cy = max(0, min(mask_height - 1, int(cyf)))
-        return [cx, cy], [cxf - cx, cyf - cy], False, []
+        center, loc_off = [cx, cy], [cxf - cx, cyf - cy]
+        if box3d is None:
+            return center, loc_off, False, []
+        pts = np.asarray(box3d, dtype=np.float64).reshape(8, 2)
+        top, bottom = pts[[0, 3, 4, 7]], pts[[1, 2, 5, 6]]            # corner order of the reference (:76-77)
+        i_left, i_right = int(np.argmin(bottom[:, 0])), int(np.argmax(bottom[:, 0]))   # first extremum, like np.argmin/argmax
+        rest = [i for i in range(4) if i not in (i_left, i_right)]    # the masked-array argmax of :83-87: first maximum in y
+        i_mid = max(rest, key=lambda i: bottom[i, 1])
+        bottom_left, bottom_right, bottom_center = bottom[i_left], bottom[i_right], bottom[i_mid]
+        if bottom_center[1] < min(bottom_left[1], bottom_right[1]):   # :90-93 (non-convex projection)
+            center_height = box2d[3]
+            bottom_center = bottom_right
+        else:
+            center_height = bottom_center[1] - top[i_mid][1]
+        cp = np.asarray([cxf, cyf]) * R                                # :98
+        offs = [bottom_left - cp, bottom_center - cp, bottom_right - cp]
+        to_center = np.asarray([R * mask_width * 0.5, R * mask_height * 0.5])
+        valid = all(np.sum(np.abs(o - to_center)) <= R * mask_width * 2 for o in (offs[0], offs[2], offs[1]))   # :107-115
+        return center, loc_off, valid, [offs[0], offs[1], offs[2], center_height]
 
-    def filter_objects(self, objects, img_w, img_h):
-        """clip + MIN_BOX_AREA filter (reference processor.py:241-253): kept boxes, their class ids, ignore areas."""
-        boxes, cls, ignore = [], [], []
+    def extra_targets(self, obj, bbox, mask_width, mask_height):
+        """The l_shape (7) / 3d_info (5) regression targets of one kept object in channel order (reference :296-299), or
+        None when the L-shape is active but not valid: the object then becomes an ignore area (:283-285)."""
+        fields = self.params.REGRESSION_FIELDS
+        vals = []
+        if fields["l_shape"].active:
+            box3d = obj["box3d"] if obj.get("box3d_valid") else None
+            _, _, valid, ls = self.calc_img_data(bbox, box3d, mask_width, mask_height)
+            if not valid:
+                return None
+            vals += [*ls[0], *ls[1], *ls[2], ls[3]]
+        if fields["3d_info"].active:
+            import math
+            vals += [math.sqrt(obj["x"] ** 2 + obj["y"] ** 2 + obj["z"] ** 2), obj["orientation"], obj["width"], obj["height"],
+                     obj["length"]]
+        return vals
+
+    def filter_objects(self, objects, img_w, img_h, extras=None):
+        """clip + MIN_BOX_AREA filter (reference processor.py:241-253): kept boxes, their class ids, ignore areas.  With the
+        l_shape / 3d_info fields active, `extras` (a list) receives each kept object's extra targets, and objects without a
+        valid L-shape join the ignore areas (:283-285)."""
+        p = self.params
+        want_extra = extras is not None and (p.REGRESSION_FIELDS["l_shape"].active or p.REGRESSION_FIELDS["3d_info"].active)
+        mw, mh = p.INPUT_WIDTH // p.R, p.INPUT_HEIGHT // p.R
+        boxes, cls, ignore, late_ignore = [], [], [], []
         for obj in objects:
             cb = self.clip_to_img(obj["box2d"], 0, 0, img_w, img_h)
-            if cb[2] * cb[3] > self.params.MIN_BOX_AREA:
+            if cb[2] * cb[3] > p.MIN_BOX_AREA:
+                if want_extra:
+                    ex = self.extra_targets(obj, cb, mw, mh)
+                    if ex is None:
+                        late_ignore.append(cb)
+                        continue
+                    extras.append(ex)
                 boxes.append(cb)
                 c = obj["obj_class"]
                 cls.append(OD_CLASS_IDX[c] if isinstance(c, str) else int(c))
             else:
                 ignore.append(cb)
-        return boxes, cls, ignore
+        return boxes, cls, ignore + late_ignore
+
+    def extra_layout(self):
+        """(first channel, channel count) of the l_shape / 3d_info block in y_true, (0, 0) when neither is active."""
+        p = self.params
+        keys = [k for k in ("l_shape", "3d_info") if p.REGRESSION_FIELDS[k].active]
+        if not keys:
+            return 0, 0
+        return p.start_idx(keys[0]), sum(p.REGRESSION_FIELDS[k].size for k in keys)
 
     # -- fast path ------------------------------------------------------------------------------------------------------
     def render_batch(self, samples, out=None, extra_ignore=None):
@@ -113,14 +166,17 @@ class ProcessImages(IPreProcessor):
         p = self.params
         L = layout_from_params(p)
         b_boxes, b_cls, b_ign = [], [], []
+        ex_off, ex_n = self.extra_layout()
+        extras = [] if ex_n else None
         for i, s in enumerate(samples):
-            boxes, cls, ign = self.filter_objects(s["objects"], p.INPUT_WIDTH, p.INPUT_HEIGHT)
+            boxes, cls, ign = self.filter_objects(s["objects"], p.INPUT_WIDTH, p.INPUT_HEIGHT, extras)
             if extra_ignore is not None:
                 ign = ign + list(extra_ignore[i])
             b_boxes.append(boxes)
             b_cls.append(cls)
             b_ign.append(ign)
-        return self.render_packed(L, *pack_objects(b_boxes, b_cls), *pack_boxes(b_ign), out=out)
+        extra = np.asarray(extras, dtype=np.float32).reshape(-1, ex_n) if ex_n else None
+        return self.render_packed(L, *pack_objects(b_boxes, b_cls), *pack_boxes(b_ign), out=out, extra=extra, extra_off=ex_off)
 
     def render_raw_batch(self, raw_boxes, raw_cls, raw_offsets, out=None, raw_track=None):
         """Device-resident raw labels -> y_true, no host loop: raw_boxes [n,4] float64 CUDA (x, y, w, h in input px, NOT
@@ -132,14 +188,15 @@ class ProcessImages(IPreProcessor):
                                                      p.MIN_BOX_AREA, raw_track)
         return ops.render_gt(L, objs, offs, int(raw_offsets.numel()) - 1, ign, ioffs, out=out)
 
-    def render_packed(self, L, rec, offsets, ign_rec, ign_offsets, out=None):
+    def render_packed(self, L, rec, offsets, ign_rec, ign_offsets, out=None, extra=None, extra_off=0):
         dev = self.device
         B = len(offsets) - 1
         objs_d = ops.to_device_records(rec, ops.OBJ_DTYPE, dev)
         offs_d = torch.from_numpy(offsets).to(dev, non_blocking=True)
         ign_d = ops.to_device_records(ign_rec, ops.BOX_DTYPE, dev)
         ioffs_d = torch.from_numpy(ign_offsets).to(dev, non_blocking=True)
-        return ops.render_gt(L, objs_d, offs_d, B, ign_d, ioffs_d, out=out)
+        extra_d = torch.from_numpy(np.ascontiguousarray(extra)).to(dev, non_blocking=True) if extra is not None and len(extra) else None
+        return ops.render_gt(L, objs_d, offs_d, B, ign_d, ioffs_d, out=out, extra=extra_d, extra_off=extra_off)
 
     # -- reference plug-in entry point -----------------------------------------------------------------------------------
     def process(self, raw_data, input_data, ground_truth, piped_params=None):

@@ -105,8 +105,10 @@ def prepare_objects(raw_boxes, raw_cls, raw_offsets, img_w, img_h, min_box_area,
 
 
 # ---- render ----------------------------------------------------------------------------------------------------------
-def render_gt(layout: Layout, objs_dev, obj_offsets_dev, B, ignore_dev=None, ign_offsets_dev=None, out=None):
-    """y_true [B,H,W,Ct] from device object records (see pack in models/centernet/processor.py)."""
+def render_gt(layout: Layout, objs_dev, obj_offsets_dev, B, ignore_dev=None, ign_offsets_dev=None, out=None, extra=None,
+              extra_off=0):
+    """y_true [B,H,W,Ct] from device object records (see pack in models/centernet/processor.py).
+    extra: optional float32 CUDA [n_obj, n] of per-object targets (l_shape / 3d_info) for channels [extra_off, extra_off+n)."""
     _need_cuda(objs_dev, "objs")
     _need_cuda(obj_offsets_dev, "obj_offsets", torch.int32)
     if out is None:
@@ -115,6 +117,15 @@ def render_gt(layout: Layout, objs_dev, obj_offsets_dev, B, ignore_dev=None, ign
     if tuple(out.shape) != (B, layout.H, layout.W, layout.Ct) or not out.is_contiguous():
         raise _lib.CvmError("out must be a contiguous [B,H,W,Ct] tensor")
     s = layout.c_struct()
+    if extra is not None and extra.numel() > 0:
+        _need_cuda(extra, "extra", torch.float32)
+        if extra.dim() != 2 or not extra.is_contiguous():
+            raise _lib.CvmError("extra must be a contiguous [n_obj, n] float32 tensor")
+        rc = _lib.lib().cvm_render_gt_extra(C.byref(s), _ptr(objs_dev), _ptr(obj_offsets_dev), _ptr(ignore_dev),
+                                            _ptr(ign_offsets_dev), B, _ptr(extra), int(extra.shape[1]), int(extra_off),
+                                            int(extra.shape[1]), _ptr(out), _stream())
+        _lib.check(rc, "cvm_render_gt_extra")
+        return out
     rc = _lib.lib().cvm_render_gt(C.byref(s), _ptr(objs_dev), _ptr(obj_offsets_dev), _ptr(ignore_dev),
                                   _ptr(ign_offsets_dev), B, _ptr(out), _stream())
     _lib.check(rc, "cvm_render_gt")

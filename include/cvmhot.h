@@ -120,6 +120,13 @@ int cvm_prepare_objects(const double* raw_boxes, const int32_t* raw_cls, const f
  * scatter: last writer wins).  ignore / ign_offsets may be NULL.  y_true is [B,H,W,Ct], fully overwritten. */
 int cvm_render_gt(const cvm_layout* L, const cvm_obj* objs, const int32_t* obj_offsets, const cvm_box* ignore,
                   const int32_t* ign_offsets, int B, float* y_true, void* stream);
+/* cvm_render_gt plus per-object extra regression targets - l_shape (7 floats) and / or 3d_info (5 floats), computed on
+ * the host from the 3D box (processor.py:69-115) - scattered to channels [extra_off, extra_off + extra_n) of the centre
+ * pixel like the other targets (processor.py:296-299; last writer wins).  extra: device [n_obj][extra_stride] floats in
+ * object order. */
+int cvm_render_gt_extra(const cvm_layout* L, const cvm_obj* objs, const int32_t* obj_offsets, const cvm_box* ignore,
+                        const int32_t* ign_offsets, int B, const float* extra, int extra_stride, int extra_off, int extra_n,
+                        float* y_true, void* stream);
 /* One plane [B,H,W,1], no weights, records use (cx, cy, w, h, peak) with CVM_OBJ_EXPLICIT_CENTER semantics. */
 int cvm_render_prev_hm(const cvm_layout* L, const cvm_obj* objs, const int32_t* obj_offsets, int B, float* prev_hm,
                        void* stream);

@@ -51,6 +51,46 @@ def gen_render_process(r, seed, n_obj, in_w, in_h):
                 R=P.R, alpha=P.VARIANCE_ALPHA)
 
 
+def gen_render_process_3d(r, seed, n_obj, in_w, in_h):
+    """Real ProcessImages.process with the l_shape and 3d_info fields active (processor.py:69-115,283-299): objects with a
+    projected 3D box (8 corners), some without (-> ignore areas), some with a far-off / non-convex projection."""
+    import cv2
+    P = r["CenternetParams"](6)
+    P.INPUT_WIDTH, P.INPUT_HEIGHT = in_w, in_h
+    P.REGRESSION_FIELDS["l_shape"].active = True
+    P.REGRESSION_FIELDS["3d_info"].active = True
+    proc = r["ProcessImages"](P)
+    ok, buf = cv2.imencode(".png", np.zeros((in_h, in_w, 3), np.uint8))
+    rng = np.random.default_rng(seed)
+    boxes, cls, valid, box3d, info = [], [], [], [], []
+    for i in range(n_obj):
+        w = float(np.exp(rng.uniform(np.log(6), np.log(in_w / 3))))
+        h = float(np.exp(rng.uniform(np.log(6), np.log(in_h / 2))))
+        x, y = float(rng.uniform(-10, in_w - 8)), float(rng.uniform(-8, in_h - 8))
+        boxes.append([x, y, w, h])
+        cls.append(int(rng.integers(0, 6)))
+        valid.append(i % 5 != 2)
+        # 8 corners: front face (0..3) and back face (4..7), top = 0,3,4,7 / bottom = 1,2,5,6 (processor.py:76-77)
+        dx, dy = rng.uniform(-0.3, 0.3) * w, rng.uniform(-0.15, 0.15) * h
+        front = [[x, y], [x, y + h], [x + 0.7 * w, y + h * rng.uniform(0.85, 1.1)], [x + 0.7 * w, y]]
+        back = [[x + dx + 0.3 * w, y + dy], [x + dx + 0.3 * w, y + dy + 0.8 * h], [x + dx + w, y + dy + 0.8 * h], [x + dx + w, y + dy]]
+        pts = np.array(front + back, np.float64)
+        if i % 7 == 4:
+            pts += 4 * in_w                                  # projection far outside: invalid L-shape (:107-115)
+        if i % 7 == 5:
+            pts[[2, 5, 6], 1] = y + h * 1.2                   # the middle bottom point above both others: the non-convex branch (:90-93)
+            pts[1, 1] = y + h * 1.3
+        box3d.append(pts.reshape(-1))
+        info.append([float(rng.uniform(-20, 20)), float(rng.uniform(-2, 2)), float(rng.uniform(3, 80)), float(rng.uniform(-3.1, 3.1)),
+                     float(rng.uniform(1.4, 2.6)), float(rng.uniform(1.2, 3.5)), float(rng.uniform(2.5, 12))])
+    objs = [{"box2d": b, "obj_class": NAMES[c], "box3d_valid": bool(v), "box3d": list(map(float, k)), "x": t[0], "y": t[1], "z": t[2],
+             "orientation": t[3], "width": t[4], "height": t[5], "length": t[6]}
+            for b, c, v, k, t in zip(boxes, cls, valid, box3d, info)]
+    _, _, gt, _ = proc.process({"img": buf.tobytes(), "objects": objs}, None, None, {"epoch": 0})
+    return dict(raw_boxes=np.array(boxes, np.float64), cls=np.array(cls, np.int32), valid=np.array(valid), box3d=np.array(box3d, np.float64),
+                info=np.array(info, np.float64), y_true=gt.astype(np.float32), in_w=in_w, in_h=in_h)
+
+
 def gen_fill_cases(r, seed):
     """Real fill_heatmap (processor.py:17-38): explicit centres (also outside the map) and peaks < 1."""
     H, W = 40, 56
@@ -253,6 +293,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "render_process_a.npz"), **gen_render_process(r, 11, 14, 192, 96))
     np.savez_compressed(os.path.join(HERE, "render_process_b.npz"), **gen_render_process(r, 12, 40, 256, 128))
     np.savez_compressed(os.path.join(HERE, "render_process_empty.npz"), **gen_render_process(r, 13, 0, 64, 32))
+    np.savez_compressed(os.path.join(HERE, "render_process_3d.npz"), **gen_render_process_3d(r, 14, 30, 256, 128))
     np.savez_compressed(os.path.join(HERE, "fill_cases.npz"), **gen_fill_cases(r, 21))
     np.savez_compressed(os.path.join(HERE, "decode_r.npz"), **gen_decode_r(r, 31))
     np.savez_compressed(os.path.join(HERE, "to3.npz"), **gen_to3(r, 41))

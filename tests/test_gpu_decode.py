@@ -232,3 +232,36 @@ def test_window9_vs_oracle(cuda, H, W, nb):
             assert np.array_equal(out["centers"][b, :n].cpu().numpy(), np.array([o["center"] for o in ref], np.float32))
             assert np.array_equal(out["boxes"][b, :n].cpu().numpy(), np.array([o["fullbox"] for o in ref], np.float32))
             assert np.array_equal(out["scores"][b, :n].cpu().numpy(), np.array([o["score"] for o in ref], np.float32))
+
+
+def test_topk_wrong_prediction_takes_the_exact_slow_path(cuda):
+    """The scan kernel starts every image from a threshold PREDICTED from the image before it (and from the previous call,
+    through the workspace).  A batch of high-scoring maps followed by low-scoring ones of the same shape makes every
+    prediction too high: the merge kernel must notice (fewer than K published peaks reach the provisional threshold) and
+    recompute those images exactly.  Results never depend on the prediction."""
+    from cvmhot import ops
+    from cvmhot.models.centernet.post_processing import decode_topk
+    H, W, C, B = 64, 96, 10, 6
+    Lo = make_layout(H, W, C, "N")
+    rng = np.random.default_rng(21)
+    hot = np.zeros((B, H, W, Lo.Cp), np.float32)
+    hot[..., :C] = rng.uniform(0.5, 0.999, (B, H, W, C)).astype(np.float32)
+    hot[..., C:] = rng.uniform(0, 50, (B, H, W, Lo.Cp - C)).astype(np.float32)
+    cold = hot.copy()
+    cold[..., :C] = rng.uniform(0.0, 0.2, (B, H, W, C)).astype(np.float32)
+    cold[1, ..., :C] = 0.0                                   # no positive value at all
+    cold[2, 5, 7, 3] = 0.9                                   # one lonely high peak
+    p = _params(C, True, H, W)
+    for _ in range(2):                                       # leaves a high prediction in the workspace
+        out = decode_topk(torch.from_numpy(hot).to(cuda), p, K=100)
+    _check_topk(out, decode_np.decode_topk(Lo, hot, 100), 100)
+    n0 = ops.decode_fallback_count()
+    out = decode_topk(torch.from_numpy(cold).to(cuda), p, K=100)
+    assert ops.decode_fallback_count() > n0                  # the slow path ran ...
+    _check_topk(out, decode_np.decode_topk(Lo, cold, 100), 100)   # ... and the result is exact
+    mixed = np.concatenate([hot[:2], cold[:2], hot[2:4], cold[2:4]])          # inside one call: hot images predict for cold ones
+    out = decode_topk(torch.from_numpy(mixed).to(cuda), p, K=100)
+    _check_topk(out, decode_np.decode_topk(Lo, mixed, 100), 100)
+    big = np.tile(mixed, (8, 1, 1, 1))                       # 64 images: several images per CTA, predictions chain inside a CTA
+    out = decode_topk(torch.from_numpy(big).to(cuda), p, K=100)
+    _check_topk(out, decode_np.decode_topk(Lo, big, 100), 100)

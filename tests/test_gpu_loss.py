@@ -183,7 +183,9 @@ def test_backward_vs_autograd(cuda, profile, track, allf, K, H, W):
     assert float(out.detach()) == pytest.approx(float(ref.detach()), rel=RTOL)
     g, gr = yp_d.grad.cpu().double(), yp64.grad
     scale = gr.abs().max()
-    assert torch.allclose(g, gr, rtol=1e-4, atol=float(scale) * 1e-6)
+    # fp64 autograd of the fp64 restatement = the analytic gradient; 1e-5 relative (north_star), with an absolute floor of
+    # 1e-6 of the largest entry for the elements that are differences of nearly equal terms
+    assert torch.allclose(g, gr, rtol=1e-5, atol=float(scale) * 1e-6)
 
 
 def test_backward_full_size_fast_equals_generic(cuda, monkeypatch):

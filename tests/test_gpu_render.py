@@ -205,3 +205,28 @@ def test_device_front_end_vs_real_process_golden(cuda, golden_dir):
         goti = ign_d.cpu().numpy()[:irec.size * ops.BOX_DTYPE.itemsize].view(ops.BOX_DTYPE)
         for f in ("x", "y", "w", "h"):
             assert np.array_equal(goti[f], irec[f]), f
+
+
+def test_render_l_shape_and_3d_info_vs_real_process_golden(cuda, golden_dir):
+    """l_shape (7) and 3d_info (5) targets active (reference processor.py:69-115,283-299): objects without a valid L-shape
+    turn into ignore areas, the non-convex projection takes the box height; y_true equals the REAL process() output."""
+    from cvmhot.models.centernet import ProcessImages
+    g = np.load(os.path.join(golden_dir, "render_process_3d.npz"))
+    names = ["car", "truck", "van", "motorbike", "cyclist", "ped"]
+    p = _params(6, False, int(g["in_h"]) // 2, int(g["in_w"]) // 2)
+    p.REGRESSION_FIELDS["l_shape"].active = True
+    p.REGRESSION_FIELDS["3d_info"].active = True
+    assert p.mask_channels() + 1 == g["y_true"].shape[-1]
+    objs = [{"box2d": list(b), "obj_class": names[c], "box3d_valid": bool(v), "box3d": list(k), "x": t[0], "y": t[1], "z": t[2],
+             "orientation": t[3], "width": t[4], "height": t[5], "length": t[6]}
+            for b, c, v, k, t in zip(g["raw_boxes"], g["cls"], g["valid"], g["box3d"], g["info"])]
+    proc = ProcessImages(p)
+    y = proc.render_batch([{"objects": objs}, {"objects": objs[:7]}])
+    y0 = y[0].cpu().numpy()
+    assert (y0 == g["y_true"]).mean() == 1.0
+    _, _, gt, _ = proc.process({"img": np.zeros((int(g["in_h"]), int(g["in_w"]), 3), np.uint8), "objects": objs}, None, None, {"epoch": 0})
+    assert np.array_equal(gt, g["y_true"])
+    # the loss mirror consumes these targets (all fields active)
+    from cvmhot.models.centernet import CenternetLoss
+    yp = torch.rand((2,) + tuple(y.shape[1:3]) + (p.mask_channels(),), device=cuda)
+    assert torch.isfinite(CenternetLoss(p)(y, yp))
