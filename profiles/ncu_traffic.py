@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-launch DRAM traffic of every kernel in an `ncu --set full` report -> profiles/traffic.json
+"""(round 1 helper; round 2 writes profiles/traffic.json per config, see profiles/README.md) Per-launch DRAM traffic of every kernel in an `ncu --set full` report -> profiles/traffic.json
 (dram__bytes_read.sum + dram__bytes_write.sum, bytes; the last launch of each kernel name wins).
 usage: python profiles/ncu_traffic.py <rep> [<rep> ...]"""
 import csv
