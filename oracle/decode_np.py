@@ -4,7 +4,7 @@ Profile R (the reference as shipped):
   process_2d_output     /root/reference/models/centernet/post_processing.py:6-66
   convert_back_to_roi   /root/reference/common/utils/image.py:22-28
   `decode_window9` is a vectorised restatement and is validated against the REAL function
-  (tests/test_oracle_vs_reference.py, tests/golden/decode_r_*.npz).
+  (tests/test_oracle_golden.py::test_live_reference_random, tests/golden/decode_r.npz).
 
 Profile N (what BASELINE.json's north_star specifies; SURVEY.md App. A.3.2 — there is no such code
 in the reference, so parity for it is defined by this file and is otherwise UNPINNED):

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY — CPU restatement of the semseg colour/argmax step.
 
 Follows `to_3channel`, /root/reference/common/utils/image.py:72-100, vectorised over pixels.
-Validated against the REAL numba function in tests/test_oracle_vs_reference.py and the fixtures
+Validated against the REAL numba function in tests/test_oracle_golden.py::test_live_reference_random and the fixtures
 tests/golden/to3_*.npz. Behaviour pinned there: ties -> first index; an all-equal
 row with apply_softmax=True becomes 0/0 = NaN -> argmax 0; NaN fails `> threshold`; the uint8 cast
 truncates. Unlike the reference this restatement does NOT mutate its input (image.py:82 does, quirk C.9).

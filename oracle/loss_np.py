@@ -8,12 +8,15 @@ op by op from the source:
   CentertrackerLoss              /root/reference/models/centertracker/loss.py:16-28
   MultitaskLoss.calc_centernet   /root/reference/models/multitask/loss.py:21-24,44-47
 
-PARITY UNPINNED by the reference's own tests: loss_test.py holds only inequalities, several of them
-stale against the current class-CE loss. What pins this restatement:
-  * the reference fixtures (loss_test.py:9-49, centertracker/loss_test.py:10-21) are re-used as inputs and
-    the still-valid inequalities are asserted (tests/test_oracle_loss.py);
-  * the derived values of SURVEY.md App. C.1 (0.27574 / 0.28467 / 0.28311 / 4.88091) are regenerated;
-  * an independent torch-CPU fp32 restatement (written separately, `loss_torch32`) must agree to 1e-5.
+PINNED TO THE REFERENCE SOURCE (round 2): oracle/tf_shim.py supplies TensorFlow's ops over torch-CPU fp32, so the
+UNMODIFIED reference files run line by line (oracle/ref_import.py); tests/golden/make_golden.py stores their outputs in
+tests/golden/loss_*.npz (the reference's own fixtures of loss_test.py:9-49 and centertracker/loss_test.py:10-21 with the
+perturbations its tests apply, Profile R / N at 128x384, tracker layouts, all fields, no objects, clip edges, the
+multitask slice) and tests/test_oracle_loss_golden.py holds every term of this restatement to them within 1e-5
+relative.  (The reference's own tests carry no numeric expectations: inequalities only, several stale against the
+current class-CE loss; the still-valid ones and the derived values 0.27574 / 0.28467 / 0.28311 /
+4.88091 are asserted in tests/test_oracle_loss.py, and an independently written torch fp32 twin, `loss_torch32`, must
+agree to 1e-5.)
 TF semantics honoured: tf.equal/tf.less on fp32 values; pow on the UNclipped prediction; clip only inside
 log; categorical_crossentropy(from_logits=True) = -sum_c t_c*log_softmax(p)_c with labels not
 renormalised; multiply_no_nan; tf.cond(n>0, ..); every reduction runs over all axes including batch.
