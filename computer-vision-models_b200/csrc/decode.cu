@@ -37,7 +37,13 @@
 
 namespace {
 
-constexpr int kTestWarps = 6;      // threads [0, kTestThreads): tester warps (they share named barrier 1)
+#ifndef CVM_TEST_WARPS
+#define CVM_TEST_WARPS 6
+#endif
+#ifndef CVM_POLL_NS
+#define CVM_POLL_NS 32
+#endif
+constexpr int kTestWarps = CVM_TEST_WARPS;      // threads [0, kTestThreads): tester warps (they share named barrier 1)
 constexpr int kScanWarps = 8;
 constexpr int kTestThreads = kTestWarps * 32;
 constexpr int kLoaderWarp = kTestWarps + kScanWarps;
@@ -1242,7 +1248,7 @@ __device__ __forceinline__ void tester_main(const DecodeParams& p, long long g_f
                     gather(p, false, 0);
                 } else {
                     STAT_T0();
-                    __nanosleep(32);
+                    __nanosleep(CVM_POLL_NS);
                     SPIN_GUARD(spins, "tester waiting for records");
                     STAT_ACC(6);
                 }

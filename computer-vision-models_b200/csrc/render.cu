@@ -18,7 +18,11 @@
 // (Tried in round 2: the per-chunk integer bookkeeping - ranges, first / last row, ignore-box test, a fifth of the kernel's
 // instructions because all 32 warps of an SM repeat it - done by ONE thread a chunk ahead and read from shared memory:
 // 0.173 ms instead of 0.163; the kernel is bound by the latency of its barrier-separated phases, and the lone thread
-// lengthens exactly that.)
+// lengthens exactly that.  Also tried: more, smaller CTAs (3 x 384 threads with 44 KB chunks: 0.168 ms; 2 x 256 / 320 / 384 /
+// 448 / 512 threads: 0.173 / 0.168 / 0.158 / 0.158 / 0.159) and a pixel-parallel splat in which every thread owns pixels of
+// the chunk and walks the objects that meet its rows with plain max / min instead of warp-per-unit shared atomics: bit-exact
+// too, but 0.21-0.28 ms - 15 k window tests per chunk against 1.3 k covered cells, and the fp64 path does not fit 64
+// registers.)
 #include <stdlib.h>
 
 #include "common.cuh"
