@@ -379,7 +379,13 @@ def run_ours(args):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
-    def step(events=None):
+    side = torch.cuda.Stream(device=dev)
+
+    def step(events=None, ov=False):
+        """One pass of the path.  ov: the decode - it only reads y_pred - is issued on a second stream beside render (+ loss).
+        All kernels are persistent and fill the GPU, so they still execute one after the other, but the CTAs of the next
+        kernel start on the SMs the previous one frees instead of waiting for its last CTA (each kernel's start-up and tail
+        cost ~10 us at these batch sizes).  events (sequential schedule only): one mark per stage boundary."""
         k = 0
 
         def mark():
@@ -387,36 +393,53 @@ def run_ours(args):
             if events is not None:
                 events[k].record()
             k += 1
-        mark()
+
+        def decode():
+            if args.config == 5:
+                return ops.decode_topk(L, y_pred_cn, K=TOPK, semseg=(14, 5))
+            return ops.decode_topk(L, y_pred, K=TOPK)
+
+        main = torch.cuda.current_stream(dev)
         out = None
+        if ov:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                out = decode()
+        mark()
         if args.config == 2:
             ops.render_gt(L, inp["objs_d"], inp["offs_d"], B, inp["ign_d"], inp["ioffs_d"], out=y_true)
             mark()
             if world == 1:
                 ops.loss_total(L, y_true, y_pred, True, partials=partials, out=loss_out)     # one launch
                 mark()
-                out = ops.decode_topk(L, y_pred, K=TOPK)
+                if not ov:
+                    out = decode()
             else:
                 ops.loss_partials(L, y_true, y_pred, True, out=partials)
                 # the one collective of the path: 16 doubles per rank, gathered while the decode kernel runs and summed in
                 # rank order (bit-reproducible whatever the collective's algorithm)
                 work = dist.all_gather_into_tensor(gathered.view(-1), partials, async_op=True)
                 mark()
-                out = ops.decode_topk(L, y_pred, K=TOPK)
+                if not ov:
+                    out = decode()
                 work.wait()
                 ops.loss_finalize_gathered(L, gathered, partials=partials, out=loss_out)     # rank-ordered sum + finalise: one launch
         elif args.config == 4:
             ops.render_prev_heatmap(L, inp["objs_d"], inp["offs_d"], B, out=prev_hm)
             mark()
-            out = ops.decode_topk(L, y_pred, K=TOPK)
-        else:
-            out = ops.decode_topk(L, y_pred_cn, K=TOPK, semseg=(14, 5))
+            if not ov:
+                out = decode()
+        elif not ov:
+            out = decode()
         mark()
+        if ov:
+            main.wait_stream(side)
         return out
 
     n_marks = len(names) + 1
+    overlap = bool(args.overlap) and args.config in (2, 4)
     for _ in range(max(args.warmup, 3)):
-        out = step()
+        out = step(ov=overlap)
     torch.cuda.synchronize()
 
     def barrier():
@@ -428,16 +451,32 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    stage_events = [[ev() for _ in range(n_marks)] for _ in range(args.steps)]
     barrier()
     e0, e1 = ev(), ev()
     e0.record()
     for k in range(args.steps):
-        out = step(stage_events[k])
+        out = step(ov=overlap)
     e1.record()
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
-    stage_ms = np.array([[s[i].elapsed_time(s[i + 1]) for i in range(n_marks - 1)] for s in stage_events]).mean(axis=0)
+
+    # ---- per-stage durations (roofline attribution): the same step in the sequential schedule, one event per stage boundary.
+    #      (With the decode on its own stream the stages interleave and cannot be told apart; `value` is the overlapped run.) ----
+    n_stage_steps = max(3, min(args.steps, 10))
+    stage_events = [[ev() for _ in range(n_marks)] for _ in range(n_stage_steps)]
+    for _ in range(2):
+        step()
+    barrier()
+    s0, s1 = ev(), ev()
+    s0.record()
+    for k in range(n_stage_steps):
+        out = step(stage_events[k])
+    s1.record()
+    barrier()
+    sequential_ms = s0.elapsed_time(s1) / n_stage_steps
+    # (median over the steps: a host-side hiccup - allocator, garbage collection - between two launches of one step would
+    # otherwise be booked on whichever stage was waiting for its launch)
+    stage_ms = np.median(np.array([[s[i].elapsed_time(s[i + 1]) for i in range(n_marks - 1)] for s in stage_events]), axis=0)
 
     # ---- the backward of the loss as its own timed stage (config 2; not part of the metric: reads y_true + y_pred, writes the gradient) ----
     extra = {}
@@ -583,7 +622,9 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["workload"], "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"dp{world} (batch shards" + (", one 128-byte exchange overlapped with decode)" if args.config == 2 else ", no collective)"),
-                   "l2": f"inputs larger than L2 ({y_pred.numel() * 4 / 1e6:.0f} MB y_pred per GPU per step)"},
+                   "l2": f"inputs larger than L2 ({y_pred.numel() * 4 / 1e6:.0f} MB y_pred per GPU per step)",
+                   "schedule": ("decode on a second stream beside render + loss (it only reads y_pred); per-stage times from a "
+                                f"separate sequential pass of the same step ({sequential_ms:.4f} ms/step)") if overlap else "one stream, stages back to back"},
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": load_traffic(names[dom].split("(")[0], args.config), "peak_source": peak_src,
                      "whole_step_gbs": whole, "whole_step_frac": whole / peak_gbs, "stages": stages},
@@ -614,6 +655,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
     ap.add_argument("--chunks", type=int, default=4, help="e2e leg: H2D chunks per step")
     ap.add_argument("--spare-sms", type=int, default=-1, help="SMs the decode leaves to the collective (default: 2 when N > 1)")
+    ap.add_argument("--overlap", type=int, default=1, help="configs 2 / 4: 1 = decode on a second stream beside render (+ loss); 0 = one stream")
     ap.add_argument("--check", action="store_true", help="N > 1: compare the sharded loss partials with one GPU, bit for bit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
