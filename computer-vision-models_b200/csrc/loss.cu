@@ -407,8 +407,10 @@ __global__ void __launch_bounds__(kFastThreads + 32) loss_fwd_fast_kernel(const 
         int s = 0;
         uint32_t e_parity = 0;
         for (int it = 0;; ++it) {
-            const long long span = blockIdx.x + (long long)it * gstride;
-            if (span >= p.n_spans) break;
+            // spans are walked from the END of the tensors: y_true has just been written by the render in the usual pipeline,
+            // and the last ~100 MB of it are still in L2 (126 MB) - read those first, before the stream evicts them
+            const long long span = p.n_spans - 1 - (blockIdx.x + (long long)it * gstride);
+            if (span < 0) break;
             if (it >= n_stages) mbar_wait(&empty_bar[s], e_parity);
             float* dst_t = ring + (size_t)s * stage_floats;
             float* dst_p = dst_t + t_floats;
@@ -445,8 +447,10 @@ __global__ void __launch_bounds__(kFastThreads + 32) loss_fwd_fast_kernel(const 
         int folded = 0, s = 0;
         uint32_t f_parity = 0;
         for (int it = 0;; ++it) {
-            const long long span = blockIdx.x + (long long)it * gstride;
-            if (span >= p.n_spans) break;
+            // spans are walked from the END of the tensors: y_true has just been written by the render in the usual pipeline,
+            // and the last ~100 MB of it are still in L2 (126 MB) - read those first, before the stream evicts them
+            const long long span = p.n_spans - 1 - (blockIdx.x + (long long)it * gstride);
+            if (span < 0) break;
             const long long left = p.n_pixels - span * TP;
             const int np = left < TP ? (int)left : TP;
             mbar_wait(&full_bar[s], f_parity);
