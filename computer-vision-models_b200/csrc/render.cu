@@ -36,20 +36,40 @@ namespace {
 #else
 #define RDBG(bit) 0
 #endif
-constexpr int kThreads = 512;
-constexpr int kWarps = kThreads / 32;
-constexpr int kMaxObjSmem = 64;   // objects are processed in batches of this many
-constexpr int kMaxIgnSmem = 16;     // ignore boxes cached in shared memory per image (more are read from global)
-#ifndef CVM_RENDER_CHUNK
-#define CVM_RENDER_CHUNK 81920
+// Builder groups (see render_kernel): kGroups groups of kGT threads with a kBufBytes staging buffer each, plus one setup
+// group of kGT threads.
+#ifndef CVM_RENDER_GROUPS
+#define CVM_RENDER_GROUPS 5
+#endif
+#ifndef CVM_RENDER_GT
+#define CVM_RENDER_GT 128
+#endif
+#ifndef CVM_RENDER_BUF
+#define CVM_RENDER_BUF 32768
 #endif
 #ifndef CVM_RENDER_COLTAB
-#define CVM_RENDER_COLTAB 1536   /* the 32 objects of BASELINE configs[1] need ~1350 column entries; 80 KB chunks make room: 0.1606 -> 0.1571 ms */
+#define CVM_RENDER_COLTAB 1536   /* the 32 objects of BASELINE configs[1] need ~1350 column entries */
 #endif
-constexpr int kChunkBytes = CVM_RENDER_CHUNK;   // staging buffer per CTA (two CTAs per SM: one builds while the other's chunk streams out)
-constexpr int kMaxUnits = 512;       // (object, 32-column segment) work units per chunk and object batch
-constexpr int kColTab = CVM_RENDER_COLTAB;        // entries of the per-image column-factor table (objects that do not fit use exp)
-constexpr int kRowTab = 1024;        // entries of the per-image row-factor table
+#ifdef CVM_R_NOINLINE
+#define CVM_R_COLD __noinline__
+#else
+#define CVM_R_COLD __forceinline__
+#endif
+#ifdef CVM_R_NOSYM
+#define RABS(v) (v)
+#else
+#define RABS(v) abs(v)
+#endif
+constexpr int kGroups = CVM_RENDER_GROUPS;
+constexpr int kGT = CVM_RENDER_GT;            // threads per group (>= kMaxObjSmem: one thread per object in the scatter)
+constexpr int kGW = kGT / 32;                 // warps per group
+constexpr int kThreads = (kGroups + 1) * kGT;
+constexpr int kBufBytes = CVM_RENDER_BUF;     // staging buffer per builder group
+constexpr int kMaxObjSmem = 64;    // objects with tabulated factors per image (later ones evaluate exp per cell)
+constexpr int kMaxIgnSmem = 16;    // ignore boxes cached in shared memory per image (more are read from global)
+constexpr int kColTab = CVM_RENDER_COLTAB;    // entries of the per-image column-factor table (objects that do not fit use exp)
+constexpr int kRowTab = 1024;      // entries of the per-image row-factor table
+static_assert(kGT >= kMaxObjSmem && kGT % 32 == 0, "one thread per tabulated object");
 
 struct RenderParams {
     const cvm_obj* objs;
@@ -89,9 +109,13 @@ struct ObjDerived {
     int last_at_pixel;      // no later object scatters to the same pixel
     int tab;                // start of the object's column factors in the table, -1 if they did not fit
     int tabr;               // start of the object's row factors in the table, -1 if they did not fit
+    int lox, nx;            // the factors are even in the distance to the centre: entries for |x - cx| in [lox, lox + nx)
+    int loy, ny;
+    int pad[2];             // 136 bytes: a stride of 128 would put the same field of all objects into one shared-memory bank
 };
 
-__device__ __forceinline__ void derive(const cvm_obj& o, const RenderParams& p, ObjDerived& d) {
+// (not inlined, like everything else off the builders' hot loop: the loop has to stay resident in the instruction cache)
+__device__ CVM_R_COLD void derive(const cvm_obj& o, const RenderParams& p, ObjDerived& d) {
     const double w = o.w, h = o.h;
     int cx, cy;
     d.scx = -1;
@@ -137,6 +161,18 @@ __device__ __forceinline__ void derive(const cvm_obj& o, const RenderParams& p, 
     d.plane = p.per_class ? o.cls : 0;
     if (d.plane < 0 || d.plane >= p.n_planes) d.x1 = d.x0;            // class out of range: draw nothing
     d.last_at_pixel = 1;
+    // distances |x - cx| that occur in the window (the centre of an explicit object may lie outside the map)
+    d.lox = d.loy = d.nx = d.ny = 0;
+    if (d.x0 < d.x1 && d.y0 < d.y1) {
+#ifdef CVM_R_NOSYM
+        d.lox = d.x0 - cx; d.nx = d.x1 - d.x0; d.loy = d.y0 - cy; d.ny = d.y1 - d.y0;
+#else
+        d.lox = cx < d.x0 ? d.x0 - cx : (cx >= d.x1 ? cx - (d.x1 - 1) : 0);
+        d.nx = max(cx - d.x0, d.x1 - 1 - cx) - d.lox + 1;
+        d.loy = cy < d.y0 ? d.y0 - cy : (cy >= d.y1 ? cy - (d.y1 - 1) : 0);
+        d.ny = max(cy - d.y0, d.y1 - 1 - cy) - d.loy + 1;
+#endif
+    }
 }
 
 // shared -> global bulk copy (bytes % 16 == 0, both addresses 16-byte aligned), tracked by the issuing thread's bulk groups
@@ -146,284 +182,391 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-extern __shared__ __align__(128) unsigned char g_render_smem[];   // the staging buffer (kChunkBytes)
+extern __shared__ __align__(128) unsigned char g_render_smem[];   // RenderShared, then the staging buffers of the groups
+#ifdef CVM_EXPERIMENT
+__device__ unsigned long long g_render_dbg[12];   // cycles of group leaders per phase (tools/time_render.py)
+#define RCLK(i)                                  \
+    {                                            \
+        const long long now_ = clock64();        \
+        dbg_t[i] += now_ - dbg_last;             \
+        dbg_last = now_;                         \
+    }
+#else
+#define RCLK(i)
+#endif
 
-// max / min combine of a float into shared memory through integer atomics on the bit pattern: non-negative floats order
-// like signed ints, negative floats order inversely like unsigned ints, and each of the two operations keeps the cell
-// monotone in float order, so any interleaving of them ends at the true max / min.
-__device__ __forceinline__ void smem_max_float(float* cell, float v) {
-    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(cell), __float_as_int(v));
-    else atomicMin(reinterpret_cast<unsigned int*>(cell), __float_as_uint(v));
-}
-__device__ __forceinline__ void smem_min_float(float* cell, float v) {
-    if (v >= 0.f) atomicMin(reinterpret_cast<int*>(cell), __float_as_int(v));
-    else atomicMax(reinterpret_cast<unsigned int*>(cell), __float_as_uint(v));
-}
-
-// The gaussian is separable: exp(-(ax + ay)) = exp(-ax) * exp(-ay).  The column factors exp(-ax) of every object are
+// Per-image state, built by the setup group one image ahead of the builders (two sets, image parity picks one).
+// The gaussian is separable: exp(-(ax + ay)) = exp(-ax) * exp(-ay).  The column factors exp(-ax) of every object
 // and its row factors exp(-ay) are tabulated once per image, so a covered pixel costs one fp64 multiply instead
 // of one fp64 exp.  The product differs from the exp of the sum by a few ulp of a DOUBLE; after the rounding to fp32
 // that the reference stores, the value is the same except when a rounding boundary falls inside that interval
 // (probability ~1e-8 per value), where it differs by one fp32 ulp -- far inside the 1e-5 tolerance.
-__global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_constant__ RenderParams p) {
-    __shared__ ObjDerived sobj[kMaxObjSmem];
-    __shared__ double s_col[kColTab];                   // column factors, object after object
-    __shared__ double s_row[kRowTab];                   // row factors, object after object
-    __shared__ int s_unit[kMaxUnits];                   // work units: object (low 8 bits) | 32-column segment of its window
-    __shared__ int s_nunits[2];                         // double-buffered by list-build parity (reset one build ahead)
-    __shared__ int s_ign[kMaxIgnSmem][4];               // ignore boxes of the image: sx, ex, sy, ey (clamped to the map)
-    __shared__ unsigned char s_own[kColTab + kRowTab];   // object that owns each table entry
-    __shared__ int s_used[2];                            // table entries in use (columns, rows)
+struct TableSet {
+    ObjDerived obj[kMaxObjSmem];
+    int4 win[kMaxObjSmem];             // x0, x1, y0, y1 of every object again: what the builders' window test reads (lane = object)
+    double col[kColTab];               // column factors, object after object
+    double row[kRowTab];               // row factors, object after object
+    int ign[kMaxIgnSmem][4];           // ignore boxes of the image: sx, ex, sy, ey (clamped to the map)
+    int o_begin, o_end, n, i_begin, n_ign, pad[3];
+};
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+struct RenderShared {
+    TableSet set[2];
+    unsigned char own[kColTab + kRowTab];   // (setup scratch) object that owns each table entry
+    int used[2];                            // (setup scratch) table entries in use (columns, rows)
+    volatile int ready;                     // images of this CTA, counted from its first one, whose table set is complete
+    volatile int prog[kGroups];             // image (same counting) each builder group is working in
+};
+
+__device__ __forceinline__ void bar_group(int id, int nt) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nt) : "memory"); }
+__device__ __forceinline__ void fence_cta_r() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+#define RENDER_SPIN(cond)                          \
+    {                                              \
+        unsigned spins_ = 0;                       \
+        while (!(cond)) {                          \
+            __nanosleep(32);                       \
+            if (++spins_ > (1u << 24)) __trap();   \
+        }                                          \
+    }
+
+// ---- per-image tables: derived records, scatter winners, ignore boxes, gaussian factors.  Run by `nt` threads (st = 0 ..
+//      nt - 1, nt >= kMaxObjSmem) that share the named barrier `bar_id` ----
+__device__ CVM_R_COLD void setup_image(const RenderParams& p, RenderShared& S, TableSet& T, int img, int st, int nt, int bar_id) {
+#define BAR() bar_group(bar_id, nt)
+    const int W = p.W;
+    const bool scatter = p.off_class >= 0 || p.off_roff >= 0 || p.off_box >= 0 || p.off_track >= 0 || p.extra_n > 0;
+    const int o_begin = p.obj_offsets[img], o_end = p.obj_offsets[img + 1];
+    const int n = min(kMaxObjSmem, o_end - o_begin);
+    int n_ign = 0, i_begin = 0;
+    if (p.ignore != nullptr && p.wch >= 0) {
+        i_begin = p.ign_offsets[img];
+        n_ign = p.ign_offsets[img + 1] - i_begin;
+    }
+    if (st < min(n_ign, kMaxIgnSmem)) {
+        const cvm_box bx = p.ignore[i_begin + st];
+        T.ign[st][0] = max((int)bx.x, 0);
+        T.ign[st][1] = min(max((int)(bx.x + bx.w), 0), W);
+        T.ign[st][2] = max((int)bx.y, 0);
+        T.ign[st][3] = min(max((int)(bx.y + bx.h), 0), p.H);
+    }
+    if (st < n) {
+        derive(p.objs[o_begin + st], p, T.obj[st]);
+        T.win[st] = make_int4(T.obj[st].x0, T.obj[st].x1, T.obj[st].y0, T.obj[st].y1);
+    }
+    BAR();
+    if (st < n && scatter) {
+        // a later object (list order) on the same centre pixel overwrites r_offset / fullbox / track_offset
+        // (processor.py:288-299), so only the last one writes them
+        const int sx = T.obj[st].scx, sy = T.obj[st].scy;
+        bool last = true;
+        for (int j = st + 1; o_begin + j < o_end && last; ++j) {
+            if (j < n) {
+                if (T.obj[j].scx == sx && T.obj[j].scy == sy) last = false;
+            } else {
+                ObjDerived e;
+                derive(p.objs[o_begin + j], p, e);
+                if (e.scx == sx && e.scy == sy) last = false;
+            }
+        }
+        T.obj[st].last_at_pixel = last;
+    }
+    if (st < n) {   // table space in object order; an object that does not fit evaluates exp per cell
+        int off = 0, offr = 0;
+        for (int o = 0; o < st; ++o) {
+            off += T.obj[o].nx;
+            offr += T.obj[o].ny;
+        }
+        const int wd = T.obj[st].nx, ht = T.obj[st].ny;
+        const int tab = off + wd <= kColTab ? off : -1, tabr = offr + ht <= kRowTab ? offr : -1;
+        // owner of every table entry, so that the factors can be computed one entry per thread
+        if (tab >= 0)
+            for (int e = 0; e < wd; ++e) S.own[tab + e] = (unsigned char)st;
+        if (tabr >= 0)
+            for (int e = 0; e < ht; ++e) S.own[kColTab + tabr + e] = (unsigned char)st;
+        if (st == n - 1) {
+            S.used[0] = tab >= 0 ? tab + wd : 0;      // (the last object fits only if all before it did)
+            S.used[1] = tabr >= 0 ? tabr + ht : 0;
+        }
+        T.obj[st].tab = tab;
+        T.obj[st].tabr = tabr;
+    }
+    if (n == 0 && st == 0) S.used[0] = S.used[1] = 0;
+    BAR();
+    if (n > 0 && (T.obj[n - 1].tab < 0 || T.obj[n - 1].tabr < 0)) {
+        // some object did not fit: its entries are not tabulated, the entries before it are found by scanning
+        if (st == 0) {
+            int used = 0, usedr = 0;
+            for (int o = 0; o < n; ++o) {
+                if (T.obj[o].tab >= 0) used = T.obj[o].tab + T.obj[o].nx;
+                if (T.obj[o].tabr >= 0) usedr = T.obj[o].tabr + T.obj[o].ny;
+            }
+            S.used[0] = used;
+            S.used[1] = usedr;
+        }
+        BAR();
+    }
+    const int used = S.used[0], usedr = S.used[1];
+    for (int e = st; e < used + usedr; e += nt) {
+        if (e < used) {
+            const ObjDerived& d = T.obj[S.own[e]];
+            const double dx = (double)(d.lox + (e - d.tab));
+            T.col[e] = exp(-(dx * dx * d.inv2vx));
+        } else {
+            const int r = e - used;
+            const ObjDerived& d = T.obj[S.own[kColTab + r]];
+            const double dy = (double)(d.loy + (r - d.tabr));
+            T.row[r] = exp(-(dy * dy * d.inv2vy));
+        }
+    }
+    if (st == 0) {
+        T.o_begin = o_begin;
+        T.o_end = o_end;
+        T.n = n;
+        T.i_begin = i_begin;
+        T.n_ign = n_ign;
+    }
+#undef BAR
+}
+
+// ---- the setup group: the tables of the CTA's images, one image ahead of the builders (the first image was prepared by
+//      the whole CTA) ----
+__device__ __forceinline__ void setup_main(const RenderParams& p, RenderShared& S, int st, int img0, int n_img) {
+#ifndef CVM_R_NO_ALLSETUP
+    for (int k = 1; k < n_img; ++k) {
+#else
+    for (int k = 0; k < n_img; ++k) {
+#endif
+        if (k >= 2 && st == 0) {   // the set still holds image k - 2: every builder group must have left it
+            for (int g = 0; g < kGroups; ++g) RENDER_SPIN(S.prog[g] >= k - 1);
+            fence_cta_r();
+        }
+        bar_group(kGroups + 1, kGT);
+        setup_image(p, S, S.set[k & 1], img0 + k, st, kGT, kGroups + 1);
+        fence_cta_r();
+        bar_group(kGroups + 1, kGT);   // (also: S.own / S.used are free for the next image)
+        if (st == 0) S.ready = k + 1;
+    }
+}
+
+// One object into the pixels [s0, s1) of the image that ONE warp owns (a piece of the chunk that starts at pixel q0; rows
+// ysa..ysb): lane = column.  Nobody else touches these cells during the splat, so the max / min combine is a plain
+// read-modify-write - no shared atomics (they retire at 2 cycles per LANE on this SM and were the kernel's bottleneck).
+// TAB: both factors come from the image's tables (col / row); otherwise exp per cell where a table is missing.
+template <bool TAB>
+__device__ __forceinline__ void splat_rows(const RenderParams& p, const ObjDerived& d, const double* col, const double* row,
+                                           float* st, int q0, int s0, int s1, int ysa, int ysb, int lane) {
+    const int x0 = d.x0, x1 = d.x1, cx = d.cx, cy = d.cy;
+    const bool has_tab = TAB || (col && d.tab >= 0), has_tabr = TAB || (row && d.tabr >= 0);
+    const int tab = d.tab - d.lox, tabr = d.tabr - d.loy;
+    const int r0 = max(d.y0, ysa), r1 = min(d.y1, ysb + 1);
+    const double peak = d.peak, rw = d.rw, inv2vx = d.inv2vx, inv2vy = d.inv2vy;
+    const int W = p.W, Cout = p.Cout, wch = p.wch;
+    float* const plane_px = st + d.plane;
+    for (int y = r0; y < r1; ++y) {
+        const int rs = y * W;
+        const int cs = max(x0, s0 - rs), ce = min(x1, s1 - rs);   // the part of the window's row inside [s0, s1)
+        if (cs >= ce) continue;
+        double ey;
+        if (has_tabr) {
+            ey = row[tabr + RABS(y - cy)];
+        } else {
+            const double dy = (double)(y - cy);
+            ey = exp(-(dy * dy * inv2vy));
+        }
+        for (int x = cs + lane; x < ce; x += 32) {
+            double ex;
+            if (has_tab) {
+                ex = col[tab + RABS(x - cx)];
+            } else {
+                const double dx = (double)(x - cx);
+                ex = exp(-(dx * dx * inv2vx));
+            }
+            const double gv = ex * ey;                                           // processor.py:34-36
+            float* const cell = plane_px + (rs + x - q0) * Cout;
+            *cell = fmaxf(*cell, (float)(gv * peak));                            // :37
+            if (wch >= 0) {
+                float* const wc = st + (rs + x - q0) * Cout + wch;
+                *wc = fminf(*wc, (float)(1.0 - rw * gv));                        // :38
+            }
+        }
+    }
+    __syncwarp();   // the next object of this warp may meet the same cells from other lanes
+}
+__device__ CVM_R_COLD void splat_object_slow(const RenderParams& p, const ObjDerived& d, const double* col, const double* row,
+                                               float* st, int q0, int s0, int s1, int ysa, int ysb, int lane) {
+    splat_rows<false>(p, d, col, row, st, q0, s0, s1, ysa, ysb, lane);
+}
+__device__ __forceinline__ void splat_object(const RenderParams& p, const ObjDerived& d, const double* col, const double* row,
+                                             float* st, int q0, int s0, int s1, int ysa, int ysb, int lane) {
+    if (d.tab >= 0 && d.tabr >= 0) splat_rows<true>(p, d, col, row, st, q0, s0, s1, ysa, ysb, lane);
+    else splat_object_slow(p, d, col, row, st, q0, s0, s1, ysa, ysb, lane);
+}
+
+// centre scatter of one object: regression targets and the class one-hot live in channels the splat never touches
+__device__ __forceinline__ void scatter_object(const RenderParams& p, const ObjDerived& d, int obj_index, float* st, int q0,
+                                               int q1) {
+    const int qs = d.scy * p.W + d.scx;
+    if (d.scx < 0 || qs < q0 || qs >= q1) return;
+    float* px = st + (size_t)(qs - q0) * p.Cout;
+    if (p.off_class >= 0 && d.cls >= 0 && p.off_class + d.cls < p.Cout) px[p.off_class + d.cls] = 1.0f;   // :290
+    if (!d.last_at_pixel) return;
+    if (p.off_roff >= 0) {
+        px[p.off_roff] = d.offx;                                                                         // :292
+        px[p.off_roff + 1] = d.offy;
+    }
+    if (p.off_box >= 0) {
+        px[p.off_box] = d.bw;                                                                            // :294
+        px[p.off_box + 1] = d.bh;
+    }
+    if (p.off_track >= 0) {
+        px[p.off_track] = d.tx;
+        px[p.off_track + 1] = d.ty;
+    }
+    if (p.extra_n > 0) {   // l_shape (7) / 3d_info (5) targets, computed on the host (processor.py:69-115,296-299)
+        const float* e = p.extra + (size_t)obj_index * p.extra_stride;
+        for (int k = 0; k < p.extra_n; ++k) px[p.extra_off + k] = e[k];
+    }
+}
+
+// objects beyond the tabulated ones (crowded images; rare): derived on the fly, exp per cell; every warp walks all of them
+// for its own pixels
+__device__ CVM_R_COLD void splat_extra_objects(const RenderParams& p, float* st, int o_begin, int o_end, int q0, int q1, int s0,
+                                                 int s1, int ysa, int ysb, int lane) {
+    const bool scatter = p.off_class >= 0 || p.off_roff >= 0 || p.off_box >= 0 || p.off_track >= 0 || p.extra_n > 0;
+    for (int j = o_begin + kMaxObjSmem; j < o_end; ++j) {
+        ObjDerived d;
+        derive(p.objs[j], p, d);
+        d.tab = d.tabr = -1;
+        if (d.x0 < d.x1 && max(d.y0, ysa) < min(d.y1, ysb + 1)) splat_object_slow(p, d, nullptr, nullptr, st, q0, s0, s1, ysa, ysb, lane);
+        const int qs = d.scy * p.W + d.scx;
+        if (scatter && d.scx >= 0 && qs >= s0 && qs < s1) {   // warp-uniform: the warp that owns the centre pixel
+            bool later = false;
+            for (int j2 = j + 1 + lane; j2 < o_end; j2 += 32) {
+                ObjDerived e;
+                derive(p.objs[j2], p, e);
+                later |= e.scx == d.scx && e.scy == d.scy;
+            }
+            d.last_at_pixel = !__any_sync(0xffffffffu, later);
+            if (lane == 0) scatter_object(p, d, j, st, q0, q1);
+        }
+    }
+}
+
+// ---- a builder group: fill -> splat -> scatter -> ignore areas -> one bulk store, chunk after chunk ----
+__device__ __forceinline__ void builder_main(const RenderParams& p, RenderShared& S, float* st, int g, int gt, long long c0,
+                                             long long c1, int img0) {
+    const int lane = gt & 31, wg = gt >> 5;
     const int W = p.W, HW = p.HW, Cout = p.Cout, wch = p.wch, P = p.P, cpi = p.cpi;
     const bool has_w = wch >= 0;
-    float* const stage0 = reinterpret_cast<float*>(g_render_smem);
-
-    const long long G = gridDim.x, g = blockIdx.x;
-    const long long c0 = g * p.n_chunks / G, c1 = (g + 1) * p.n_chunks / G;
+    const int bar_id = 1 + g;
     // pattern fill: thread t < n_fill writes the float4s t, t + n_fill, ...; n_fill is a multiple of Cout, so the channel
     // phase of its float4 -- and with it the value (zeros, 1.0 where the weights channel falls) -- never changes
-    const int n_fill = (kThreads / Cout) * Cout;
+    const int n_fill = (kGT / Cout) * Cout;
     float4 fill_v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (has_w) {
-        const int r = (4 * tid) % Cout;   // channel of the first float of this thread's float4s
+        const int r = (4 * gt) % Cout;   // channel of the first float of this thread's float4s
         fill_v.x = ((r + 0) % Cout == wch) ? 1.f : 0.f;
         fill_v.y = ((r + 1) % Cout == wch) ? 1.f : 0.f;
         fill_v.z = ((r + 2) % Cout == wch) ? 1.f : 0.f;
         fill_v.w = ((r + 3) % Cout == wch) ? 1.f : 0.f;
     }
     const bool scatter = p.off_class >= 0 || p.off_roff >= 0 || p.off_box >= 0 || p.off_track >= 0 || p.extra_n > 0;
-    int loaded_img = -1;         // image whose per-image state (ranges, ignore boxes, first object batch) is loaded
-    int loaded_base = -1;        // first object of the batch in sobj
-    int o_begin = 0, o_end = 0, i_begin = 0, n_ign = 0, n_batches = 0;
-    int lk = 0;                  // list builds so far (parity picks the counter)
-    const int step_rows = P / W, step_cols = P - step_rows * W;   // how (ya, xa) advance from one chunk to the next
-    if (tid < 2) s_nunits[tid] = 0;
-    __syncthreads();
-
-    int img = (int)(c0 / cpi);
-    int ci = (int)(c0 - (long long)img * cpi);
-    int ya = (ci * P) / W, xa = ci * P - ya * W;   // row / column of the chunk's first pixel, kept incrementally
-    const int n_local = (int)(c1 - c0);
-    for (int it = 0; it < n_local; ++it) {
+    int cur_rel = -1;
+#ifdef CVM_EXPERIMENT
+    long long dbg_t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, dbg_last = clock64();
+#endif
+    // (image, chunk in image) of the group's first chunk; advanced by kGroups chunks per iteration without divisions
+    int img = (int)((c0 + g) / cpi), ci = (int)((c0 + g) - (long long)img * cpi);
+    for (long long c = c0 + g; c < c1; c += kGroups) {
+        const int rel = img - img0;
         const int q0 = ci * P, q1 = min(HW, q0 + P), npx = q1 - q0;
-        int yb = ya;   // row of the chunk's last pixel
+        const int ya = q0 / W, xa = q0 - ya * W;   // row / column of the chunk's first pixel
+        int yb = ya;                               // row of its last pixel
         for (int t = xa + npx - 1; t >= W; t -= W) ++yb;
-        float* const st = stage0;
-        const bool new_img = loaded_img != img;
-        if (new_img) {   // object / ignore-box ranges of the image: fetched once per image, not once per chunk
-            o_begin = p.obj_offsets[img];
-            o_end = p.obj_offsets[img + 1];
-            n_batches = (o_end - o_begin + kMaxObjSmem - 1) / kMaxObjSmem;
-            n_ign = i_begin = 0;
-            if (p.ignore != nullptr && has_w) {
-                i_begin = p.ign_offsets[img];
-                n_ign = p.ign_offsets[img + 1] - i_begin;
+        if (gt == 0) {
+            if (rel != cur_rel) {   // (every reader of the previous image's set passed the last barrier of its last chunk)
+                fence_cta_r();
+                S.prog[g] = rel;
             }
+            if (p.bulk) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous chunk has left the buffer
+        }
+        RCLK(0);
+        bar_group(bar_id, kGT);   // ---- barrier C: the buffer is free ----
+        RCLK(1);
+        // ---- phase 1: pattern fill (heat = 0, weights = 1, regression targets = 0; processor.py:267-268) ----
+        if (gt < n_fill && !RDBG(4)) {
+            const int n4 = (npx * Cout + 3) >> 2;   // the buffer is a whole number of float4s
+            float4* s4 = reinterpret_cast<float4*>(st);
+#ifndef CVM_R_NOUNROLL
+#pragma unroll 4
+#endif
+            for (int f = gt; f < n4; f += n_fill) s4[f] = fill_v;
+        }
+        RCLK(2);
+        if (rel != cur_rel) {
+            if (gt == 0) {   // the image's tables (built by the setup group while this group filled)
+                RENDER_SPIN(S.ready > rel);
+                fence_cta_r();
+            }
+            cur_rel = rel;
+        }
+        RCLK(3);
+        bar_group(bar_id, kGT);   // ---- barrier A: the fill is complete, the table set is visible ----
+        RCLK(4);
+        const TableSet& T = S.set[rel & 1];
+        const int n = T.n, o_begin = T.o_begin, o_end = T.o_end, n_ign = T.n_ign, i_begin = T.i_begin;
+
+        // ---- phase 2: every warp owns a contiguous quarter of the chunk's pixels and max/min-combines into it every
+        //      object that meets its rows (found with a ballot, lane = object), one after the other ----
+        if (!RDBG(1)) {
+            const int per = (npx + kGW - 1) / kGW;
+            const int s0 = q0 + wg * per, s1 = min(q1, s0 + per);
+#ifdef CVM_R_DIV
+            const int ysa = s0 / W, ysb = (s1 - 1) / W;
+#else
+            int ysa = ya, ysb;   // rows of the first and last pixel of the piece
+            int t = xa + wg * per;
+            for (; t >= W; t -= W) ++ysa;
+            ysb = ysa;
+            for (t += s1 - s0 - 1; t >= W; t -= W) ++ysb;
+#endif
+            if (s0 < s1) {
+                for (int b0 = 0; b0 < n; b0 += 32) {
+                    const int o = b0 + lane;
+                    bool meets = false;
+                    if (o < n) {   // does the window meet this warp's pixels?  (row by row: the piece may start / end inside a row)
+                        const int4 w = T.win[o];
+                        for (int y = max(w.z, ysa), ye = min(w.w, ysb + 1); y < ye && !meets; ++y)
+                            meets = max(w.x, s0 - y * W) < min(w.y, s1 - y * W);
+                    }
+                    unsigned m = __ballot_sync(0xffffffffu, meets);
+#ifdef CVM_EXPERIMENT
+                    RCLK(8);
+                    dbg_t[9] += __popc(m);
+#endif
+                    while (m) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        splat_object(p, T.obj[b0 + b], T.col, T.row, st, q0, s0, s1, ysa, ysb, lane);
+                    }
+                }
+            }
+            RCLK(10);
+            if (scatter && gt < n) scatter_object(p, T.obj[gt], o_begin + gt, st, q0, q1);
+            if (o_end - o_begin > kMaxObjSmem && s0 < s1) splat_extra_objects(p, st, o_begin, o_end, q0, q1, s0, s1, ysa, ysb, lane);
         }
 
-        if (new_img) {   // clamp the ignore boxes once per image (read after the barriers below)
-            if (tid < min(n_ign, kMaxIgnSmem)) {
-                const cvm_box bx = p.ignore[i_begin + tid];
-                s_ign[tid][0] = max((int)bx.x, 0);
-                s_ign[tid][1] = min(max((int)(bx.x + bx.w), 0), W);
-                s_ign[tid][2] = max((int)bx.y, 0);
-                s_ign[tid][3] = min(max((int)(bx.y + bx.h), 0), p.H);
-            }
-        }
-
-
-        // The pre-work of a chunk - per-image tables and the chunk's work units, nothing that touches the staging buffer -
-        // runs BEFORE the wait for the buffer, i.e. while the bulk store of the previous chunk is still reading it (every
-        // reader of these arrays finished before barrier B of the previous chunk).  Batches after the first one of a
-        // crowded image (rare) do the same work inline.
-        for (int bi = 0;; ++bi) {
-            const bool have = bi < n_batches;
-            const int base = o_begin + bi * kMaxObjSmem;
-            const int n = have ? min(kMaxObjSmem, o_end - base) : 0;
-            const int par = have ? (lk++) & 1 : 0;
-            if (have) {
-                if (new_img || loaded_base != base) {
-                    // ---- once per image (and object batch): derived records, scatter winners, column factors ----
-                    if (bi > 0) __syncthreads();   // the previous batch is still being read
-                    if (tid < n) derive(p.objs[base + tid], p, sobj[tid]);
-                    __syncthreads();
-                    if (tid < n && scatter) {
-                        // a later object (list order) on the same centre pixel overwrites r_offset / fullbox / track_offset
-                        // (processor.py:288-299), so only the last one writes them
-                        const int sx = sobj[tid].scx, sy = sobj[tid].scy;
-                        bool last = true;
-                        for (int j = base + tid + 1; j < o_end && last; ++j) {
-                            if (j - base < n) {
-                                if (sobj[j - base].scx == sx && sobj[j - base].scy == sy) last = false;
-                            } else {
-                                ObjDerived e;
-                                derive(p.objs[j], p, e);
-                                if (e.scx == sx && e.scy == sy) last = false;
-                            }
-                        }
-                        sobj[tid].last_at_pixel = last;
-                    }
-                    if (tid < n) {   // table space in object order; an object that does not fit evaluates exp per pixel
-                        int off = 0, offr = 0;
-                        for (int o = 0; o < tid; ++o) {
-                            off += max(0, sobj[o].x1 - sobj[o].x0);
-                            offr += max(0, sobj[o].y1 - sobj[o].y0);
-                        }
-                        const int wd = max(0, sobj[tid].x1 - sobj[tid].x0), ht = max(0, sobj[tid].y1 - sobj[tid].y0);
-                        const int tab = off + wd <= kColTab ? off : -1, tabr = offr + ht <= kRowTab ? offr : -1;
-                        // owner of every table entry, so that the factors can be computed one entry per thread
-                        if (tab >= 0)
-                            for (int k = 0; k < wd; ++k) s_own[tab + k] = (unsigned char)tid;
-                        if (tabr >= 0)
-                            for (int k = 0; k < ht; ++k) s_own[kColTab + tabr + k] = (unsigned char)tid;
-                        if (tid == n - 1) {
-                            s_used[0] = tab >= 0 ? tab + wd : 0;      // (the last object fits only if all before it did)
-                            s_used[1] = tabr >= 0 ? tabr + ht : 0;
-                        }
-                        sobj[tid].tab = tab;
-                        sobj[tid].tabr = tabr;
-                    }
-                    __syncthreads();
-                    if (sobj[n - 1].tab < 0 || sobj[n - 1].tabr < 0) {
-                        // some object did not fit: its entries are not tabulated, the entries before it are found by scanning
-                        if (tid == 0) {
-                            int used = 0, usedr = 0;
-                            for (int o = 0; o < n; ++o) {
-                                if (sobj[o].tab >= 0) used = sobj[o].tab + max(0, sobj[o].x1 - sobj[o].x0);
-                                if (sobj[o].tabr >= 0) usedr = sobj[o].tabr + max(0, sobj[o].y1 - sobj[o].y0);
-                            }
-                            s_used[0] = used;
-                            s_used[1] = usedr;
-                        }
-                        __syncthreads();
-                    }
-                    {
-                        const int used = s_used[0], usedr = s_used[1];
-                        for (int e = tid; e < used + usedr; e += kThreads) {
-                            if (e < used) {
-                                const ObjDerived& d = sobj[s_own[e]];
-                                const double dx = (double)(d.x0 + (e - d.tab) - d.cx);
-                                s_col[e] = exp(-(dx * dx * d.inv2vx));
-                            } else {
-                                const int r = e - used;
-                                const ObjDerived& d = sobj[s_own[kColTab + r]];
-                                const double dy = (double)(d.y0 + (r - d.tabr) - d.cy);
-                                s_row[r] = exp(-(dy * dy * d.inv2vy));
-                            }
-                        }
-                    }
-                    loaded_base = base;
-                }
-                // ---- work units of this chunk ----
-                if (tid < n && !RDBG(32)) {
-                    const ObjDerived& d = sobj[tid];
-                    if (max(d.y0, ya) < min(d.y1, yb + 1) && d.x0 < d.x1) {
-                        const int u = (d.x1 - d.x0 + 31) >> 5;
-                        const int start = atomicAdd(&s_nunits[par], u);
-                        for (int k = 0; k < u && start + k < kMaxUnits; ++k) s_unit[start + k] = tid | (k << 8);
-                    }
-                }
-                if (tid == 0) s_nunits[par ^ 1] = 0;   // the other counter is idle: reset it for the next build
-            }
-            if (bi == 0) {
-                if (p.bulk && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous chunk has left the buffer
-                __syncthreads();   // ---- barrier C: the buffer is free ----
-                // ---- phase 1: pattern fill (heat = 0, weights = 1, regression targets = 0; processor.py:267-268) ----
-                if (tid < n_fill && !RDBG(4)) {
-                    const int n4 = (npx * Cout + 3) >> 2;   // the buffer is a whole number of float4s
-                    float4* s4 = reinterpret_cast<float4*>(st);
-                    for (int f = tid; f < n4; f += n_fill) s4[f] = fill_v;
-                }
-            }
-            if (!have) break;
-            __syncthreads();   // ---- barrier A: fill, tables and units are visible ----
-
-            // ---- phase 2: one warp per (unit, row) item, lane = column; max/min-combine with shared atomics (windows of
-            //      different objects overlap).  Items are dealt round-robin to the warps; order is irrelevant ----
-            const int total = s_nunits[par];
-            const bool overflow = total > kMaxUnits;   // absurdly many wide objects: whole-object items instead
-            const int n_items = RDBG(1) ? 0 : (overflow ? n : total);
-            for (int it = warp; it < n_items; it += kWarps) {
-                const int u = overflow ? it : s_unit[it];
-                const ObjDerived& d = sobj[u & 255];
-                // the record is read ONCE: the shared atomics below are memory clobbers, anything read through `d` after
-                // them would be reloaded row after row (a chain of dependent shared loads per row)
-                const int x0 = d.x0, x1 = d.x1, y0 = d.y0, tab = d.tab, tabr = d.tabr;
-                const int r0 = max(y0, ya), r1 = min(d.y1, yb + 1);
-                float* const plane_px = st + d.plane;
-                const double peak = d.peak, rw = d.rw;
-                if (x0 >= x1) continue;
-                int xs = x0, xe = x1;
-                if (!overflow) {
-                    xs = x0 + ((u >> 8) << 5);
-                    xe = min(x1, xs + 32);
-                }
-                for (int x = xs + lane; x < xe; x += 32) {
-                    double ex;
-                    if (tab >= 0) {
-                        ex = s_col[tab + (x - x0)];
-                    } else {
-                        const double dx = (double)(x - d.cx);
-                        ex = exp(-(dx * dx * d.inv2vx));
-                    }
-                    for (int y = r0; y < r1; ++y) {
-                        const int q = y * W + x;
-                        if (q < q0 || q >= q1) continue;   // the chunk may start / end inside a row
-                        double ey;
-                        if (tabr >= 0) {
-                            ey = s_row[tabr + (y - y0)];
-                        } else {
-                            const double dy = (double)(y - d.cy);
-                            ey = exp(-(dy * dy * d.inv2vy));
-                        }
-                        const double gv = ex * ey;                                           // processor.py:34-36
-                        const int o = (q - q0) * Cout;
-                        smem_max_float(plane_px + o, (float)(gv * peak));                     // :37
-                        if (has_w) smem_min_float(st + o + wch, (float)(1.0 - rw * gv));      // :38
-                    }
-                }
-            }
-            // centre scatter: regression targets and the class one-hot live in channels the splat never touches
-            if (scatter && tid < n && !RDBG(64)) {
-                const ObjDerived& d = sobj[tid];
-                const int qs = d.scy * W + d.scx;
-                if (d.scx >= 0 && qs >= q0 && qs < q1) {
-                    float* px = st + (size_t)(qs - q0) * Cout;
-                    if (p.off_class >= 0 && d.cls >= 0 && p.off_class + d.cls < Cout) px[p.off_class + d.cls] = 1.0f;   // :290
-                    if (d.last_at_pixel) {
-                        if (p.off_roff >= 0) {
-                            px[p.off_roff] = d.offx;                                                                   // :292
-                            px[p.off_roff + 1] = d.offy;
-                        }
-                        if (p.off_box >= 0) {
-                            px[p.off_box] = d.bw;                                                                      // :294
-                            px[p.off_box + 1] = d.bh;
-                        }
-                        if (p.off_track >= 0) {
-                            px[p.off_track] = d.tx;
-                            px[p.off_track + 1] = d.ty;
-                        }
-                        if (p.extra_n > 0) {   // l_shape (7) / 3d_info (5) targets, computed on the host (processor.py:69-115,296-299)
-                            const float* e = p.extra + (size_t)(base + tid) * p.extra_stride;
-                            for (int k = 0; k < p.extra_n; ++k) px[p.extra_off + k] = e[k];
-                        }
-                    }
-                }
-            }
-        }
-
+        RCLK(5);
         // ---- phase 3: ignore areas: weights = 0, input-px numbers used as mask indices (processor.py:318-323) ----
-        bool ign_hit = n_ign > kMaxIgnSmem || (n_ign > 0 && n_batches == 0);   // (boxes beyond the cache / no barrier yet: take the slow way)
-        for (int i = 0; i < (RDBG(128) ? 0 : min(n_ign, kMaxIgnSmem)) && !ign_hit; ++i)
-            ign_hit = s_ign[i][0] < s_ign[i][1] && max(s_ign[i][2], ya) < min(s_ign[i][3], yb + 1);
-        if (ign_hit) {   // uniform: few chunks meet an ignore box
-            __syncthreads();   // all splats are in (and s_ign is visible when the image had no objects)
+        bool ign_hit = n_ign > kMaxIgnSmem;   // (boxes beyond the cache: take the slow way)
+        for (int i = 0; i < min(n_ign, kMaxIgnSmem) && !ign_hit; ++i)
+            ign_hit = T.ign[i][0] < T.ign[i][1] && max(T.ign[i][2], ya) < min(T.ign[i][3], yb + 1);
+        if (ign_hit) {   // uniform in the group: few chunks meet an ignore box
+            bar_group(bar_id, kGT);   // all splats are in
             for (int i = 0; i < n_ign; ++i) {
                 int sx, ex, sy, ey;
                 if (i < kMaxIgnSmem) {
-                    sx = s_ign[i][0], ex = s_ign[i][1], sy = s_ign[i][2], ey = s_ign[i][3];
+                    sx = T.ign[i][0], ex = T.ign[i][1], sy = T.ign[i][2], ey = T.ign[i][3];
                 } else {
                     const cvm_box bx = p.ignore[i_begin + i];
                     sx = max((int)bx.x, 0), ex = min(max((int)(bx.x + bx.w), 0), W);
@@ -433,7 +576,7 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
                 ey = min(ey, yb + 1);
                 const int bw = ex - sx, cells = bw * (ey - sy);
                 if (bw <= 0 || ey <= sy) continue;
-                for (int k = tid; k < cells; k += kThreads) {
+                for (int k = gt; k < cells; k += kGT) {
                     const int yy = sy + k / bw, xx = sx + k % bw, q = yy * W + xx;
                     if (q >= q0 && q < q1) st[(size_t)(q - q0) * Cout + wch] = 0.f;
                 }
@@ -441,51 +584,72 @@ __global__ void __launch_bounds__(kThreads, 2) render_kernel(const __grid_consta
         }
 
         // ---- stream the chunk out ----
+        float* const dst = p.out + ((size_t)img * HW + q0) * Cout;
         if (p.bulk) {
-            if (!RDBG(16)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk engine
-            __syncthreads();   // ---- barrier B: the chunk is complete ----
-            // the buffer is rebuilt only after barrier C of the next iteration (meanwhile the SM's other CTA builds its chunk)
-            if (tid == 0 && !RDBG(2)) bulk_s2g(p.out + ((size_t)img * HW + q0) * Cout, st, (uint32_t)(npx * Cout * 4));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk engine
+            RCLK(6);
+            bar_group(bar_id, kGT);   // ---- barrier B: the chunk is complete ----
+            RCLK(7);
+            if (gt == 0 && !RDBG(2)) bulk_s2g(dst, st, (uint32_t)(npx * Cout * 4));
         } else {
-            __syncthreads();
-            float* const dst = p.out + ((size_t)img * HW + q0) * Cout;
+            bar_group(bar_id, kGT);
             const int nf = npx * Cout;
-            if (p.vec) {   // 16-byte aligned chunk: 128-bit streaming stores
-                const float4* s4 = reinterpret_cast<const float4*>(st);
-                float4* d4 = reinterpret_cast<float4*>(dst);
-                for (int f = tid; f < (nf >> 2); f += kThreads) st_cs_f4(d4 + f, s4[f]);
-            } else {
-                for (int f = tid; f < nf; f += kThreads) dst[f] = st[f];
-            }
-            __syncthreads();   // the buffer is refilled two chunks later, but sobj / lists are reused by the next one
+            for (int f = gt; f < nf; f += kGT) dst[f] = st[f];   // (barrier C of the next chunk: the buffer has been read)
         }
-        loaded_img = img;
-        if (++ci == cpi) {
-            ci = 0;
+        ci += kGroups;
+        while (ci >= cpi) {
+            ci -= cpi;
             ++img;
-            ya = xa = 0;
-        } else {
-            ya += step_rows;
-            xa += step_cols;
-            if (xa >= W) {
-                xa -= W;
-                ++ya;
-            }
         }
     }
-    if (p.bulk && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA retires
+#ifdef CVM_EXPERIMENT
+    if (gt == 0)
+        for (int i = 0; i < 12; ++i) atomicAdd(&g_render_dbg[i], (unsigned long long)dbg_t[i]);
+#endif
+    if (gt == 0) {
+        fence_cta_r();
+        S.prog[g] = 0x7fffffff;   // this group reads no table set any more
+        if (p.bulk) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA retires
+    }
+}
+
+// One persistent CTA per SM owns a contiguous range of chunks (P consecutive pixels of one image, all channels).  Its
+// builder groups take the chunks of the range round-robin and never synchronise with each other (named barriers per
+// group), so while one group's bulk store drains, the others fill and splat: the store engine of the SM always has a chunk
+// queued.  The setup group prepares the per-image tables one image ahead.
+__global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_constant__ RenderParams p) {
+    RenderShared& S = *reinterpret_cast<RenderShared*>(g_render_smem);
+    constexpr size_t kStageOff = (sizeof(RenderShared) + 127) & ~(size_t)127;
+    const int tid = threadIdx.x;
+    const long long G = gridDim.x, cta = blockIdx.x;
+    const long long c0 = cta * p.n_chunks / G, c1 = (cta + 1) * p.n_chunks / G;
+    if (tid < kGroups) S.prog[tid] = 0;
+    if (c0 >= c1) return;
+    const int img0 = (int)(c0 / p.cpi), n_img = (int)((c1 - 1) / p.cpi) - img0 + 1;
+#ifndef CVM_R_NO_ALLSETUP
+    setup_image(p, S, S.set[0], img0, tid, kThreads, 0);   // the first image: all threads, nobody has anything else to do yet
+    __syncthreads();
+    if (tid == 0) S.ready = 1;
+#else
+    if (tid == 0) S.ready = 0;
+    __syncthreads();
+#endif
+    const int g = tid / kGT, gt = tid - g * kGT;
+    if (g == kGroups) setup_main(p, S, gt, img0, n_img);
+    else builder_main(p, S, reinterpret_cast<float*>(g_render_smem + kStageOff + (size_t)g * kBufBytes), g, gt, c0, c1, img0);
 }
 
 int launch_render(const RenderParams& p0, int B, cudaStream_t st) {
     RenderParams p = p0;
     p.HW = p.H * p.W;
-    int P = (kChunkBytes / (p.Cout * 4)) & ~3;
-    // narrow outputs: 4096-pixel chunks keep the (object, row) items of a chunk short; the one-channel previous-frame
-    // heatmap takes 64 KB chunks (0.121 -> 0.097 ms for the 512 images of BASELINE configs[3])
-    const int p_cap = p.Cout == 1 ? 16384 : 4096;
-    if (P > p_cap) P = p_cap;
-    if (P > ((p.HW + 3) & ~3)) P = (p.HW + 3) & ~3;
-    CVM_CHECK_ARG(P >= 4 && p.Cout <= kThreads, "render: %d output channels do not fit the staging buffer", p.Cout);
+    CVM_CHECK_ARG(p.Cout * 16 <= kBufBytes && p.Cout <= kGT, "render: %d output channels do not fit the staging buffer", p.Cout);
+    // chunks of (nearly) equal size: as few as fit the buffer, then the pixels of an image spread evenly over them
+    const int hw4 = (p.HW + 3) & ~3;
+    int pmax = (kBufBytes / (p.Cout * 4)) & ~3;
+    if (pmax > hw4) pmax = hw4;
+    const int cpi0 = (p.HW + pmax - 1) / pmax;
+    int P = ((p.HW + cpi0 - 1) / cpi0 + 3) & ~3;
+    if (P > pmax) P = pmax;
     p.P = P;
     p.cpi = (p.HW + P - 1) / P;
     p.n_chunks = (long long)B * p.cpi;
@@ -493,14 +657,13 @@ int launch_render(const RenderParams& p0, int B, cudaStream_t st) {
     // bulk stores need 16-byte granules: base aligned, every image a whole number of them (chunks are P*Cout*4 bytes with
     // P % 4 == 0, the partial last chunk of an image then ends on a granule too)
     p.bulk = cvm_aligned16(p.out) && (((long long)p.HW * p.Cout) % 4 == 0);
-    p.vec = p.bulk;
 #ifdef CVM_EXPERIMENT
     if (const char* e = getenv("CVM_RENDER_SKIP")) p.dbg_skip = atoi(e);
     if RDBG(8) p.bulk = 0;   // experiment: plain stores instead of bulk copies
 #endif
-    const size_t smem = (size_t)kChunkBytes;
+    const size_t smem = ((sizeof(RenderShared) + 127) & ~(size_t)127) + (size_t)kGroups * kBufBytes;
     CVM_SMEM_ATTR_ONCE((render_kernel), smem);
-    long long grid = 2LL * cvm_num_sms();
+    long long grid = cvm_num_sms();
     if (grid > p.n_chunks) grid = p.n_chunks;
     render_kernel<<<(unsigned)grid, kThreads, smem, st>>>(p);
     CVM_CHECK_LAUNCH("render_kernel");
@@ -508,6 +671,15 @@ int launch_render(const RenderParams& p0, int B, cudaStream_t st) {
 }
 
 }  // namespace
+
+#ifdef CVM_EXPERIMENT
+extern "C" int cvm_render_debug(unsigned long long* out8) {   // reads and clears the phase counters
+    unsigned long long z[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyFromSymbol(out8, g_render_dbg, sizeof(z));
+    cudaMemcpyToSymbol(g_render_dbg, z, sizeof(z));
+    return 0;
+}
+#endif
 
 extern "C" int cvm_render_gt(const cvm_layout* L, const cvm_obj* objs, const int32_t* obj_offsets, const cvm_box* ignore,
                              const int32_t* ign_offsets, int B, float* y_true, void* stream) {

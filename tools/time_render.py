@@ -36,3 +36,14 @@ for env in sys.argv[1:]:
     run(env)
     for kv in env.split(","):
         if kv != "-": os.environ.pop(kv.split("=")[0])
+if os.environ.get("CVM_RENDER_DBG"):
+    import ctypes
+    from cvmhot import _lib
+    lib = _lib.lib()
+    out = (ctypes.c_ulonglong * 12)()
+    lib.cvm_render_debug(out)
+    ops.render_gt(L, objs_d, offs_d, B, ign_d, ioffs_d, out=y1); torch.cuda.synchronize()
+    lib.cvm_render_debug(out)
+    names = ["loop+wait_read", "barC", "fill", "poll", "barA", "scatter", "ignore+fence", "barB", "ballot", "n_objects", "splat_objects", "-"]
+    tot = sum(out)
+    print({n: int(v / (148 * 4)) for n, v in zip(names, out)}, "cycles per group leader; total", int(tot / 592))
