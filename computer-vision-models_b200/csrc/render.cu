@@ -7,22 +7,29 @@
 // Bound: HBM writes.  Algorithmic bytes per image: 4*H*W*Ct, every byte written exactly once (zeros included).
 //
 // Structure: y_true is one flat list of chunks (P consecutive pixels of one image, all channels: a contiguous piece of
-// the NHWC tensor).  The list is cut into equal contiguous ranges, one persistent CTA per range (two per SM).  A chunk is
-// built in shared memory in its FINAL layout: a pattern fill (zeros, ones in the weights channel); then one warp per
-// (object, 32-column segment) work unit walks the unit's rows, lane = column, and max-/min-combines the gaussian into the
-// chunk with shared integer atomics on the float bit patterns (windows of different objects overlap); then ignore areas
-// and the handful of regression targets at centre pixels are written, and ONE bulk async copy (TMA engine: UBLKCP,
-// shared -> global) streams the chunk out while the SM's other CTA builds its chunk.  No store instruction
-// touches global memory on the fast path.  All gaussian math is fp64 like the reference's (scalar fp64 stored as fp32);
-// the separable factors exp(-ax), exp(-ay) are tabulated (per image / per chunk), see render_kernel.
-// (Tried in round 2: the per-chunk integer bookkeeping - ranges, first / last row, ignore-box test, a fifth of the kernel's
-// instructions because all 32 warps of an SM repeat it - done by ONE thread a chunk ahead and read from shared memory:
-// 0.173 ms instead of 0.163; the kernel is bound by the latency of its barrier-separated phases, and the lone thread
-// lengthens exactly that.  Also tried: more, smaller CTAs (3 x 384 threads with 44 KB chunks: 0.168 ms; 2 x 256 / 320 / 384 /
-// 448 / 512 threads: 0.173 / 0.168 / 0.158 / 0.158 / 0.159) and a pixel-parallel splat in which every thread owns pixels of
-// the chunk and walks the objects that meet its rows with plain max / min instead of warp-per-unit shared atomics: bit-exact
-// too, but 0.21-0.28 ms - 15 k window tests per chunk against 1.3 k covered cells, and the fp64 path does not fit 64
-// registers.)
+// the NHWC tensor, ~35 KB).  The list is cut into equal contiguous ranges, one persistent CTA per SM and range.  The CTA is
+// warp-specialised: kGroups builder groups of 4 warps, each with its own staging buffer, take the chunks of the range
+// round-robin and synchronise only inside the group (named barriers), and one setup group prepares the per-image state
+// (derived object records, "last writer" flags of the centre scatter, ignore boxes, tables of the separable gaussian
+// factors) one image ahead in a double-buffered table set.  A builder group builds a chunk in shared memory in its FINAL
+// layout: pattern fill (zeros, ones in the weights channel); then every warp OWNS a contiguous quarter of the chunk's
+// pixels and max-/min-combines into it, with plain loads and stores, every object whose window meets those pixels (found
+// with a ballot over a compact window array, lane = object; then lane = column); then the regression targets at centre
+// pixels and the ignore areas; then ONE bulk async copy (TMA engine: UBLKCP, shared -> global) streams the chunk out while
+// the other groups build theirs, so the SM's store engine always has a chunk queued.  No store instruction touches global
+// memory on the fast path.  All gaussian math is fp64 like the reference's (scalar fp64 stored as fp32).
+//
+// History (all measured on B200, 256 images of BASELINE configs[1], 755 MB): the first design (two 512-thread CTAs per SM,
+// 80 KB chunks, CTA-wide barriers between the phases, one warp per (object, 32-column segment) unit combining with SHARED
+// ATOMICS on the float bit patterns) ran at 0.162 ms.  Its limiter was not the barriers but the atomics: ATOMS retires
+// 2 cycles per LANE (B300_MICROARCH.md), 20 M of them per launch = 0.14 ms of every SM's load/store unit.  Giving each
+// warp exclusive pixels removes them: 0.218 ms (this structure with atomics) -> 0.148 -> 0.142 ms with the table / buffer
+// sizes below.  Also measured: 3 / 4 / 6 groups (0.152-0.166), 96 / 160 threads per group (slower: pieces too large /
+// register cap), cold paths out of line (__noinline__: 0.203 ms - the generic-address loads of the parameter block and
+// the call ABI cost more than the instruction-cache footprint), a 128-byte object record (a 32-way bank conflict for
+// lane = object reads: hence the 136-byte stride and the compact window array).  What is left is latency: ~100
+// instructions per (warp, object) visit at ~8 cycles each with 20 builder warps per SM; a bare bulk-store stream of the
+// same bytes takes 0.123 ms (tools/write_bench.cu).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -36,8 +43,8 @@ namespace {
 #else
 #define RDBG(bit) 0
 #endif
-// Builder groups (see render_kernel): kGroups groups of kGT threads with a kBufBytes staging buffer each, plus one setup
-// group of kGT threads.
+// Builder groups (see above): kGroups groups of kGT threads with a kBufBytes staging buffer each, plus one setup group
+// of kST threads.  80 registers per thread at 704 threads (the allocation granularity leaves no room for more warps).
 #ifndef CVM_RENDER_GROUPS
 #define CVM_RENDER_GROUPS 5
 #endif
@@ -45,31 +52,25 @@ namespace {
 #define CVM_RENDER_GT 128
 #endif
 #ifndef CVM_RENDER_BUF
-#define CVM_RENDER_BUF 32768
+#define CVM_RENDER_BUF 35840
 #endif
 #ifndef CVM_RENDER_COLTAB
-#define CVM_RENDER_COLTAB 1536   /* the 32 objects of BASELINE configs[1] need ~1350 column entries */
+#define CVM_RENDER_COLTAB 1024   /* the 32 objects of BASELINE configs[1] need ~700 column entries (mean; sd 125) */
 #endif
-#ifdef CVM_R_NOINLINE
-#define CVM_R_COLD __noinline__
-#else
-#define CVM_R_COLD __forceinline__
-#endif
-#ifdef CVM_R_NOSYM
-#define RABS(v) (v)
-#else
-#define RABS(v) abs(v)
+#ifndef CVM_RENDER_ROWTAB
+#define CVM_RENDER_ROWTAB 640    /* ... and ~500 row entries (sd 75) */
 #endif
 constexpr int kGroups = CVM_RENDER_GROUPS;
 constexpr int kGT = CVM_RENDER_GT;            // threads per group (>= kMaxObjSmem: one thread per object in the scatter)
 constexpr int kGW = kGT / 32;                 // warps per group
-constexpr int kThreads = (kGroups + 1) * kGT;
+constexpr int kST = 64;                        // threads of the setup group
+constexpr int kThreads = kGroups * kGT + kST;
 constexpr int kBufBytes = CVM_RENDER_BUF;     // staging buffer per builder group
 constexpr int kMaxObjSmem = 64;    // objects with tabulated factors per image (later ones evaluate exp per cell)
 constexpr int kMaxIgnSmem = 16;    // ignore boxes cached in shared memory per image (more are read from global)
 constexpr int kColTab = CVM_RENDER_COLTAB;    // entries of the per-image column-factor table (objects that do not fit use exp)
-constexpr int kRowTab = 1024;      // entries of the per-image row-factor table
-static_assert(kGT >= kMaxObjSmem && kGT % 32 == 0, "one thread per tabulated object");
+constexpr int kRowTab = CVM_RENDER_ROWTAB;   // entries of the per-image row-factor table
+static_assert(kGT >= kMaxObjSmem && kGT % 32 == 0 && kST >= kMaxObjSmem && kST % 32 == 0, "one thread per tabulated object");
 
 struct RenderParams {
     const cvm_obj* objs;
@@ -114,8 +115,7 @@ struct ObjDerived {
     int pad[2];             // 136 bytes: a stride of 128 would put the same field of all objects into one shared-memory bank
 };
 
-// (not inlined, like everything else off the builders' hot loop: the loop has to stay resident in the instruction cache)
-__device__ CVM_R_COLD void derive(const cvm_obj& o, const RenderParams& p, ObjDerived& d) {
+__device__ __forceinline__ void derive(const cvm_obj& o, const RenderParams& p, ObjDerived& d) {
     const double w = o.w, h = o.h;
     int cx, cy;
     d.scx = -1;
@@ -164,14 +164,10 @@ __device__ CVM_R_COLD void derive(const cvm_obj& o, const RenderParams& p, ObjDe
     // distances |x - cx| that occur in the window (the centre of an explicit object may lie outside the map)
     d.lox = d.loy = d.nx = d.ny = 0;
     if (d.x0 < d.x1 && d.y0 < d.y1) {
-#ifdef CVM_R_NOSYM
-        d.lox = d.x0 - cx; d.nx = d.x1 - d.x0; d.loy = d.y0 - cy; d.ny = d.y1 - d.y0;
-#else
         d.lox = cx < d.x0 ? d.x0 - cx : (cx >= d.x1 ? cx - (d.x1 - 1) : 0);
         d.nx = max(cx - d.x0, d.x1 - 1 - cx) - d.lox + 1;
         d.loy = cy < d.y0 ? d.y0 - cy : (cy >= d.y1 ? cy - (d.y1 - 1) : 0);
         d.ny = max(cy - d.y0, d.y1 - 1 - cy) - d.loy + 1;
-#endif
     }
 }
 
@@ -231,7 +227,7 @@ __device__ __forceinline__ void fence_cta_r() { asm volatile("fence.acq_rel.cta;
 
 // ---- per-image tables: derived records, scatter winners, ignore boxes, gaussian factors.  Run by `nt` threads (st = 0 ..
 //      nt - 1, nt >= kMaxObjSmem) that share the named barrier `bar_id` ----
-__device__ CVM_R_COLD void setup_image(const RenderParams& p, RenderShared& S, TableSet& T, int img, int st, int nt, int bar_id) {
+__device__ __forceinline__ void setup_image(const RenderParams& p, RenderShared& S, TableSet& T, int img, int st, int nt, int bar_id) {
 #define BAR() bar_group(bar_id, nt)
     const int W = p.W;
     const bool scatter = p.off_class >= 0 || p.off_roff >= 0 || p.off_box >= 0 || p.off_track >= 0 || p.extra_n > 0;
@@ -331,19 +327,15 @@ __device__ CVM_R_COLD void setup_image(const RenderParams& p, RenderShared& S, T
 // ---- the setup group: the tables of the CTA's images, one image ahead of the builders (the first image was prepared by
 //      the whole CTA) ----
 __device__ __forceinline__ void setup_main(const RenderParams& p, RenderShared& S, int st, int img0, int n_img) {
-#ifndef CVM_R_NO_ALLSETUP
     for (int k = 1; k < n_img; ++k) {
-#else
-    for (int k = 0; k < n_img; ++k) {
-#endif
         if (k >= 2 && st == 0) {   // the set still holds image k - 2: every builder group must have left it
             for (int g = 0; g < kGroups; ++g) RENDER_SPIN(S.prog[g] >= k - 1);
             fence_cta_r();
         }
-        bar_group(kGroups + 1, kGT);
-        setup_image(p, S, S.set[k & 1], img0 + k, st, kGT, kGroups + 1);
+        bar_group(kGroups + 1, kST);
+        setup_image(p, S, S.set[k & 1], img0 + k, st, kST, kGroups + 1);
         fence_cta_r();
-        bar_group(kGroups + 1, kGT);   // (also: S.own / S.used are free for the next image)
+        bar_group(kGroups + 1, kST);   // (also: S.own / S.used are free for the next image)
         if (st == 0) S.ready = k + 1;
     }
 }
@@ -368,7 +360,7 @@ __device__ __forceinline__ void splat_rows(const RenderParams& p, const ObjDeriv
         if (cs >= ce) continue;
         double ey;
         if (has_tabr) {
-            ey = row[tabr + RABS(y - cy)];
+            ey = row[tabr + abs(y - cy)];
         } else {
             const double dy = (double)(y - cy);
             ey = exp(-(dy * dy * inv2vy));
@@ -376,7 +368,7 @@ __device__ __forceinline__ void splat_rows(const RenderParams& p, const ObjDeriv
         for (int x = cs + lane; x < ce; x += 32) {
             double ex;
             if (has_tab) {
-                ex = col[tab + RABS(x - cx)];
+                ex = col[tab + abs(x - cx)];
             } else {
                 const double dx = (double)(x - cx);
                 ex = exp(-(dx * dx * inv2vx));
@@ -392,7 +384,7 @@ __device__ __forceinline__ void splat_rows(const RenderParams& p, const ObjDeriv
     }
     __syncwarp();   // the next object of this warp may meet the same cells from other lanes
 }
-__device__ CVM_R_COLD void splat_object_slow(const RenderParams& p, const ObjDerived& d, const double* col, const double* row,
+__device__ __forceinline__ void splat_object_slow(const RenderParams& p, const ObjDerived& d, const double* col, const double* row,
                                                float* st, int q0, int s0, int s1, int ysa, int ysb, int lane) {
     splat_rows<false>(p, d, col, row, st, q0, s0, s1, ysa, ysb, lane);
 }
@@ -430,7 +422,7 @@ __device__ __forceinline__ void scatter_object(const RenderParams& p, const ObjD
 
 // objects beyond the tabulated ones (crowded images; rare): derived on the fly, exp per cell; every warp walks all of them
 // for its own pixels
-__device__ CVM_R_COLD void splat_extra_objects(const RenderParams& p, float* st, int o_begin, int o_end, int q0, int q1, int s0,
+__device__ __forceinline__ void splat_extra_objects(const RenderParams& p, float* st, int o_begin, int o_end, int q0, int q1, int s0,
                                                  int s1, int ysa, int ysb, int lane) {
     const bool scatter = p.off_class >= 0 || p.off_roff >= 0 || p.off_box >= 0 || p.off_track >= 0 || p.extra_n > 0;
     for (int j = o_begin + kMaxObjSmem; j < o_end; ++j) {
@@ -497,9 +489,7 @@ __device__ __forceinline__ void builder_main(const RenderParams& p, RenderShared
         if (gt < n_fill && !RDBG(4)) {
             const int n4 = (npx * Cout + 3) >> 2;   // the buffer is a whole number of float4s
             float4* s4 = reinterpret_cast<float4*>(st);
-#ifndef CVM_R_NOUNROLL
 #pragma unroll 4
-#endif
             for (int f = gt; f < n4; f += n_fill) s4[f] = fill_v;
         }
         RCLK(2);
@@ -521,15 +511,11 @@ __device__ __forceinline__ void builder_main(const RenderParams& p, RenderShared
         if (!RDBG(1)) {
             const int per = (npx + kGW - 1) / kGW;
             const int s0 = q0 + wg * per, s1 = min(q1, s0 + per);
-#ifdef CVM_R_DIV
-            const int ysa = s0 / W, ysb = (s1 - 1) / W;
-#else
             int ysa = ya, ysb;   // rows of the first and last pixel of the piece
             int t = xa + wg * per;
             for (; t >= W; t -= W) ++ysa;
             ysb = ysa;
             for (t += s1 - s0 - 1; t >= W; t -= W) ++ysb;
-#endif
             if (s0 < s1) {
                 for (int b0 = 0; b0 < n; b0 += 32) {
                     const int o = b0 + lane;
@@ -626,16 +612,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     if (tid < kGroups) S.prog[tid] = 0;
     if (c0 >= c1) return;
     const int img0 = (int)(c0 / p.cpi), n_img = (int)((c1 - 1) / p.cpi) - img0 + 1;
-#ifndef CVM_R_NO_ALLSETUP
     setup_image(p, S, S.set[0], img0, tid, kThreads, 0);   // the first image: all threads, nobody has anything else to do yet
     __syncthreads();
     if (tid == 0) S.ready = 1;
-#else
-    if (tid == 0) S.ready = 0;
-    __syncthreads();
-#endif
     const int g = tid / kGT, gt = tid - g * kGT;
-    if (g == kGroups) setup_main(p, S, gt, img0, n_img);
+    if (g >= kGroups) setup_main(p, S, tid - kGroups * kGT, img0, n_img);
     else builder_main(p, S, reinterpret_cast<float*>(g_render_smem + kStageOff + (size_t)g * kBufBytes), g, gt, c0, c1, img0);
 }
 
