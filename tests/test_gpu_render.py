@@ -230,3 +230,37 @@ def test_render_l_shape_and_3d_info_vs_real_process_golden(cuda, golden_dir):
     from cvmhot.models.centernet import CenternetLoss
     yp = torch.rand((2,) + tuple(y.shape[1:3]) + (p.mask_channels(),), device=cuda)
     assert torch.isfinite(CenternetLoss(p)(y, yp))
+
+
+@pytest.mark.parametrize("H,W,B", [(16, 24, 1500), (40, 56, 700)])
+def test_render_many_small_images_per_cta(cuda, H, W, B):
+    """Thousands of small images: every persistent CTA walks through many images, so the setup group's double-buffered
+    table sets rotate constantly while the builder groups sit in different images.  The batch must equal the same images
+    rendered a few at a time (bitwise), and a sample must match the oracle."""
+    from cvmhot.models.centernet.processor import ProcessImages, pack_objects, pack_boxes
+    from cvmhot.layout import layout_from_params
+    K = 4
+    p = _params(K, True, H, W)
+    Lo = make_layout(H, W, K, "N")
+    L = layout_from_params(p)
+    rng = np.random.default_rng(77)
+    boxes, cls, ign = [], [], []
+    for b in range(B):
+        n = int(rng.integers(0, 9)) if b % 7 else 0          # images without objects in between
+        if b % 50 == 3:
+            n = 80                                             # ... and crowded ones (more objects than the tables hold)
+        bx, c = synth.objects_for_image(rng, H, W, 2, n, K)
+        boxes.append(bx)
+        cls.append(c)
+        ign.append(synth.ignore_for_image(rng, H, W, 20) if b % 60 == 0 else
+                   np.array([[rng.integers(0, W), rng.integers(0, H), 5, 4]], np.float64) if b % 5 == 0 else np.zeros((0, 4)))
+    proc = ProcessImages(p)
+    rec, offs = pack_objects(boxes, cls)
+    y = proc.render_packed(L, rec, offs, *pack_boxes(ign)).cpu().numpy()
+    step = 97
+    for s in range(0, B, step):
+        r2, o2 = pack_objects(boxes[s:s + step], cls[s:s + step])
+        part = proc.render_packed(L, r2, o2, *pack_boxes(ign[s:s + step])).cpu().numpy()
+        assert np.array_equal(y[s:s + step], part), s
+    for b in list(range(0, B, 131)) + [3, 53, 60, B - 1]:
+        _close(y[b], render_np.render_image(Lo, boxes[b], cls[b], ign[b]))
