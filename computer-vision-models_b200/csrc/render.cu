@@ -52,24 +52,20 @@ namespace {
 #define CVM_RENDER_GT 128
 #endif
 #ifndef CVM_RENDER_BUF
-#define CVM_RENDER_BUF 35840
+#define CVM_RENDER_BUF 34816
 #endif
-#ifndef CVM_RENDER_COLTAB
-#define CVM_RENDER_COLTAB 1024   /* the 32 objects of BASELINE configs[1] need ~700 column entries (mean; sd 125) */
-#endif
-#ifndef CVM_RENDER_ROWTAB
-#define CVM_RENDER_ROWTAB 640    /* ... and ~500 row entries (sd 75) */
+#ifndef CVM_RENDER_FACTAB
+#define CVM_RENDER_FACTAB 2048   /* the 32 objects of BASELINE configs[1] need ~1200 entries (sd 150), the ~40 of configs[3] ~1500 */
 #endif
 constexpr int kGroups = CVM_RENDER_GROUPS;
 constexpr int kGT = CVM_RENDER_GT;            // threads per group (>= kMaxObjSmem: one thread per object in the scatter)
 constexpr int kGW = kGT / 32;                 // warps per group
-constexpr int kST = 64;                        // threads of the setup group
+constexpr int kST = 128;                       // threads of the setup group
 constexpr int kThreads = kGroups * kGT + kST;
 constexpr int kBufBytes = CVM_RENDER_BUF;     // staging buffer per builder group
 constexpr int kMaxObjSmem = 64;    // objects with tabulated factors per image (later ones evaluate exp per cell)
 constexpr int kMaxIgnSmem = 16;    // ignore boxes cached in shared memory per image (more are read from global)
-constexpr int kColTab = CVM_RENDER_COLTAB;    // entries of the per-image column-factor table (objects that do not fit use exp)
-constexpr int kRowTab = CVM_RENDER_ROWTAB;   // entries of the per-image row-factor table
+constexpr int kFacTab = CVM_RENDER_FACTAB;    // entries of the per-image table of gaussian factors (objects that do not fit use exp)
 static_assert(kGT >= kMaxObjSmem && kGT % 32 == 0 && kST >= kMaxObjSmem && kST % 32 == 0, "one thread per tabulated object");
 
 struct RenderParams {
@@ -200,16 +196,15 @@ __device__ unsigned long long g_render_dbg[12];   // cycles of group leaders per
 struct TableSet {
     ObjDerived obj[kMaxObjSmem];
     int4 win[kMaxObjSmem];             // x0, x1, y0, y1 of every object again: what the builders' window test reads (lane = object)
-    double col[kColTab];               // column factors, object after object
-    double row[kRowTab];               // row factors, object after object
+    double fac[kFacTab];               // object after object: its column factors, then its row factors
     int ign[kMaxIgnSmem][4];           // ignore boxes of the image: sx, ex, sy, ey (clamped to the map)
     int o_begin, o_end, n, i_begin, n_ign, pad[3];
 };
 
 struct RenderShared {
     TableSet set[2];
-    unsigned char own[kColTab + kRowTab];   // (setup scratch) object that owns each table entry
-    int used[2];                            // (setup scratch) table entries in use (columns, rows)
+    unsigned char own[kFacTab];             // (setup scratch) object that owns each table entry
+    int used;                               // (setup scratch) table entries in use
     volatile int ready;                     // images of this CTA, counted from its first one, whose table set is complete
     volatile int prog[kGroups];             // image (same counting) each builder group is working in
 };
@@ -267,51 +262,28 @@ __device__ __forceinline__ void setup_image(const RenderParams& p, RenderShared&
         T.obj[st].last_at_pixel = last;
     }
     if (st < n) {   // table space in object order; an object that does not fit evaluates exp per cell
-        int off = 0, offr = 0;
-        for (int o = 0; o < st; ++o) {
-            off += T.obj[o].nx;
-            offr += T.obj[o].ny;
-        }
+        int off = 0;
+        for (int o = 0; o < st; ++o) off += T.obj[o].nx + T.obj[o].ny;
         const int wd = T.obj[st].nx, ht = T.obj[st].ny;
-        const int tab = off + wd <= kColTab ? off : -1, tabr = offr + ht <= kRowTab ? offr : -1;
+        const bool fits = off + wd + ht <= kFacTab;   // (then every object before it fits too)
         // owner of every table entry, so that the factors can be computed one entry per thread
-        if (tab >= 0)
-            for (int e = 0; e < wd; ++e) S.own[tab + e] = (unsigned char)st;
-        if (tabr >= 0)
-            for (int e = 0; e < ht; ++e) S.own[kColTab + tabr + e] = (unsigned char)st;
-        if (st == n - 1) {
-            S.used[0] = tab >= 0 ? tab + wd : 0;      // (the last object fits only if all before it did)
-            S.used[1] = tabr >= 0 ? tabr + ht : 0;
-        }
-        T.obj[st].tab = tab;
-        T.obj[st].tabr = tabr;
+        if (fits)
+            for (int e = 0; e < wd + ht; ++e) S.own[off + e] = (unsigned char)st;
+        T.obj[st].tab = fits ? off : -1;
+        T.obj[st].tabr = fits ? off + wd : -1;
+        if (fits && (st == n - 1 || off + wd + ht + T.obj[st + 1].nx + T.obj[st + 1].ny > kFacTab)) S.used = off + wd + ht;
     }
-    if (n == 0 && st == 0) S.used[0] = S.used[1] = 0;
+    if (st == 0 && (n == 0 || T.obj[0].nx + T.obj[0].ny > kFacTab)) S.used = 0;
     BAR();
-    if (n > 0 && (T.obj[n - 1].tab < 0 || T.obj[n - 1].tabr < 0)) {
-        // some object did not fit: its entries are not tabulated, the entries before it are found by scanning
-        if (st == 0) {
-            int used = 0, usedr = 0;
-            for (int o = 0; o < n; ++o) {
-                if (T.obj[o].tab >= 0) used = T.obj[o].tab + T.obj[o].nx;
-                if (T.obj[o].tabr >= 0) usedr = T.obj[o].tabr + T.obj[o].ny;
-            }
-            S.used[0] = used;
-            S.used[1] = usedr;
-        }
-        BAR();
-    }
-    const int used = S.used[0], usedr = S.used[1];
-    for (int e = st; e < used + usedr; e += nt) {
-        if (e < used) {
-            const ObjDerived& d = T.obj[S.own[e]];
+    const int used = S.used;
+    for (int e = st; e < used; e += nt) {
+        const ObjDerived& d = T.obj[S.own[e]];
+        if (e < d.tabr) {
             const double dx = (double)(d.lox + (e - d.tab));
-            T.col[e] = exp(-(dx * dx * d.inv2vx));
+            T.fac[e] = exp(-(dx * dx * d.inv2vx));
         } else {
-            const int r = e - used;
-            const ObjDerived& d = T.obj[S.own[kColTab + r]];
-            const double dy = (double)(d.loy + (r - d.tabr));
-            T.row[r] = exp(-(dy * dy * d.inv2vy));
+            const double dy = (double)(d.loy + (e - d.tabr));
+            T.fac[e] = exp(-(dy * dy * d.inv2vy));
         }
     }
     if (st == 0) {
@@ -533,7 +505,7 @@ __device__ __forceinline__ void builder_main(const RenderParams& p, RenderShared
                     while (m) {
                         const int b = __ffs(m) - 1;
                         m &= m - 1;
-                        splat_object(p, T.obj[b0 + b], T.col, T.row, st, q0, s0, s1, ysa, ysb, lane);
+                        splat_object(p, T.obj[b0 + b], T.fac, T.fac, st, q0, s0, s1, ysa, ysb, lane);
                     }
                 }
             }
