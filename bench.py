@@ -374,6 +374,7 @@ def _run_ours(args):
     prev_hm = torch.empty((B, Hm, Wm, 1), dtype=torch.float32, device=dev) if args.config == 4 else None
     partials = torch.empty(16, dtype=torch.float64, device=dev)
     gathered = torch.empty((world, 16), dtype=torch.float64, device=dev)
+    partials_sum = torch.zeros(16, dtype=torch.float64, device=dev)     # N > 1: the rank-ordered sum of all ranks' partials
     loss_out = torch.zeros(10, dtype=torch.float32, device=dev)
     px = Hm * Wm
     if args.config == 2:
@@ -392,6 +393,7 @@ def _run_ours(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     side = torch.cuda.Stream(device=dev)
+    comm = torch.cuda.Stream(device=dev)      # N > 1: the exchange of the loss partials and the finalise step
 
     def step(events=None, ov=False):
         """One pass of the path.  ov: the decode - it only reads y_pred - is issued on a second stream beside render (+ loss).
@@ -414,7 +416,7 @@ def _run_ours(args):
         main = torch.cuda.current_stream(dev)
         out = None
         if ov:
-            side.wait_stream(main)     # (not before the previous step is through)
+            side.wait_stream(main)     # (not before the previous step's render + loss are through)
 
         def decode_beside():
             # issued AFTER render / loss: with the main stream at high priority the decode's CTAs take the SMs those free
@@ -429,14 +431,32 @@ def _run_ours(args):
                 mark()
                 out = decode_beside() if ov else decode()
             else:
-                ops.loss_partials(L, y_true, y_pred, True, out=partials)
                 # the one collective of the path: 16 doubles per rank, gathered while the decode kernel runs and summed in
                 # rank order (bit-reproducible whatever the collective's algorithm)
-                work = dist.all_gather_into_tensor(gathered.view(-1), partials, async_op=True)
-                mark()
-                out = decode_beside() if ov else decode()
-                work.wait()
-                ops.loss_finalize_gathered(L, gathered, partials=partials, out=loss_out)     # rank-ordered sum + finalise: one launch
+                if ov:
+                    # exchange + finalise on their own stream: the main stream (render, loss) never waits for the other
+                    # ranks, so rank skew is absorbed with a step of slack instead of being paid every step
+                    if gather_done:
+                        main.wait_event(gather_done.pop())     # `partials` of the previous step has been sent
+                    ops.loss_partials(L, y_true, y_pred, True, out=partials)
+                    ready = torch.cuda.Event()
+                    ready.record(main)
+                    with torch.cuda.stream(comm):
+                        comm.wait_event(ready)
+                        dist.all_gather_into_tensor(gathered.view(-1), partials)
+                        ops.loss_finalize_gathered(L, gathered, partials=partials_sum, out=loss_out)     # rank-ordered sum + finalise: one launch
+                        sent = torch.cuda.Event()
+                        sent.record(comm)
+                        gather_done.append(sent)
+                    mark()
+                    out = decode_beside()
+                else:
+                    ops.loss_partials(L, y_true, y_pred, True, out=partials)
+                    work = dist.all_gather_into_tensor(gathered.view(-1), partials, async_op=True)
+                    mark()
+                    out = decode()
+                    work.wait()
+                    ops.loss_finalize_gathered(L, gathered, partials=partials_sum, out=loss_out)
         elif args.config == 4:
             ops.render_prev_heatmap(L, inp["objs_d"], inp["offs_d"], B, out=prev_hm)
             mark()
@@ -445,13 +465,29 @@ def _run_ours(args):
             out = decode()
         mark()
         if ov:
-            main.wait_stream(side)
+            # the main stream may run ONE step ahead of the decode stream: render n + 1 takes the SMs that decode n frees
+            # (no data flows between them; the decode only reads y_pred).  join() closes the pipeline.
+            done = torch.cuda.Event()
+            done.record(side)
+            if decode_done:
+                main.wait_event(decode_done.pop())
+            decode_done.append(done)
         return out
+
+    decode_done, gather_done = [], []
+
+    def join():
+        main = torch.cuda.current_stream(dev)
+        main.wait_stream(side)
+        main.wait_stream(comm)
+        decode_done.clear()
+        gather_done.clear()
 
     n_marks = len(names) + 1
     overlap = bool(args.overlap) and args.config in (2, 4)
     for _ in range(max(args.warmup, 3)):
         out = step(ov=overlap)
+    join()
     torch.cuda.synchronize()
 
     def barrier():
@@ -468,6 +504,7 @@ def _run_ours(args):
     e0.record()
     for k in range(args.steps):
         out = step(ov=overlap)
+    join()        # every decode of the timed steps has finished before the closing event
     e1.record()
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
@@ -495,12 +532,12 @@ def _run_ours(args):
     if args.config == 2:
         grad = torch.empty_like(y_pred)
         for _ in range(3):
-            ops.loss_backward(L, y_true, y_pred, partials, out=grad)
+            ops.loss_backward(L, y_true, y_pred, partials_sum if world > 1 else partials, out=grad)
         b0, b1 = ev(), ev()
         torch.cuda.synchronize()
         b0.record()
         for _ in range(args.steps):
-            ops.loss_backward(L, y_true, y_pred, partials, out=grad)
+            ops.loss_backward(L, y_true, y_pred, partials_sum if world > 1 else partials, out=grad)
         b1.record()
         torch.cuda.synchronize()
         bwd_ms = b0.elapsed_time(b1) / args.steps
@@ -511,7 +548,7 @@ def _run_ours(args):
     # ---- --check: the sharded partials equal the same images processed shard by shard on one GPU, bit for bit ----
     check = None
     if args.check and args.config == 2:
-        mine = partials.clone()
+        mine = (partials_sum if world > 1 else partials).clone()
         shard_parts = []
         for r_ in range(world):
             o = inp if r_ == rank else device_inputs(r_ * B, 1234 + r_)
