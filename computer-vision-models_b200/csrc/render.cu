@@ -458,7 +458,9 @@ __device__ __forceinline__ void builder_main(const RenderParams& p, RenderShared
         bar_group(bar_id, kGT);   // ---- barrier C: the buffer is free ----
         RCLK(1);
         // ---- phase 1: pattern fill (heat = 0, weights = 1, regression targets = 0; processor.py:267-268) ----
-        if (gt < n_fill && !RDBG(4)) {
+        if (Cout > kGT) {   // (very wide pixels: no thread keeps a constant channel phase; scalar fill)
+            for (int f = gt; f < npx * Cout; f += kGT) st[f] = (has_w && f % Cout == wch) ? 1.f : 0.f;
+        } else if (gt < n_fill && !RDBG(4)) {
             const int n4 = (npx * Cout + 3) >> 2;   // the buffer is a whole number of float4s
             float4* s4 = reinterpret_cast<float4*>(st);
 #pragma unroll 4
@@ -595,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
 int launch_render(const RenderParams& p0, int B, cudaStream_t st) {
     RenderParams p = p0;
     p.HW = p.H * p.W;
-    CVM_CHECK_ARG(p.Cout * 16 <= kBufBytes && p.Cout <= kGT, "render: %d output channels do not fit the staging buffer", p.Cout);
+    CVM_CHECK_ARG(p.Cout * 16 <= kBufBytes, "render: %d output channels do not fit the staging buffer", p.Cout);
     // chunks of (nearly) equal size: as few as fit the buffer, then the pixels of an image spread evenly over them
     const int hw4 = (p.HW + 3) & ~3;
     int pmax = (kBufBytes / (p.Cout * 4)) & ~3;

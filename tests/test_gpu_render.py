@@ -74,7 +74,8 @@ def test_prev_heatmap_vs_golden(cuda, golden_dir):
 
 @pytest.mark.parametrize("profile,H,W,K,track", [("N", 128, 384, 10, False), ("R", 128, 384, 10, False),
                                                  ("N", 128, 384, 10, True), ("R", 9, 11, 3, False),
-                                                 ("N", 37, 53, 7, False), ("N", 64, 1000, 4, False)])
+                                                 ("N", 37, 53, 7, False), ("N", 64, 1000, 4, False),
+                                                 ("R", 9, 11, 130, False)])   # (136-float pixels: the scalar fill)
 def test_render_vs_oracle(cuda, profile, H, W, K, track):
     from cvmhot.models.centernet.processor import ProcessImages, pack_objects, pack_boxes
     from cvmhot.layout import layout_from_params
