@@ -424,10 +424,29 @@ def _run_ours(args):
                 return decode()
         mark()
         if args.config == 2:
-            ops.render_gt(L, inp["objs_d"], inp["offs_d"], B, inp["ign_d"], inp["ioffs_d"], out=y_true)
+            piped = ov and args.overlap == 2
+            if piped:
+                # the render has its own stream and two y_true buffers: render n + 1 (the next batch's ground truth, as the
+                # reference's generator workers prepare it while the model trains) fills the SMs that loss n frees
+                i = step_no[0] % 2
+                step_no[0] += 1
+                yt = y_true_pair[i]
+                with torch.cuda.stream(rstream):
+                    if loss_done[i] is not None:
+                        rstream.wait_event(loss_done[i])      # the loss that read this buffer two steps ago
+                    ops.render_gt(L, inp["objs_d"], inp["offs_d"], B, inp["ign_d"], inp["ioffs_d"], out=yt)
+                    rendered = torch.cuda.Event()
+                    rendered.record(rstream)
+                main.wait_event(rendered)
+            else:
+                yt = y_true
+                ops.render_gt(L, inp["objs_d"], inp["offs_d"], B, inp["ign_d"], inp["ioffs_d"], out=yt)
             mark()
             if world == 1:
-                ops.loss_total(L, y_true, y_pred, True, partials=partials, out=loss_out)     # one launch
+                ops.loss_total(L, yt, y_pred, True, partials=partials, out=loss_out)     # one launch
+                if piped:
+                    loss_done[i] = torch.cuda.Event()
+                    loss_done[i].record(main)
                 mark()
                 out = decode_beside() if ov else decode()
             else:
@@ -436,22 +455,25 @@ def _run_ours(args):
                 if ov:
                     # exchange + finalise on their own stream: the main stream (render, loss) never waits for the other
                     # ranks, so rank skew is absorbed with a step of slack instead of being paid every step
-                    if gather_done:
-                        main.wait_event(gather_done.pop())     # `partials` of the previous step has been sent
-                    ops.loss_partials(L, y_true, y_pred, True, out=partials)
+                    j = xchg_no[0] % 2                         # two send / receive buffers: the loss never waits for the
+                    xchg_no[0] += 1                            # exchange of the step before, only for the one before that
+                    if gather_done[j] is not None:
+                        main.wait_event(gather_done[j])
+                    ops.loss_partials(L, yt, y_pred, True, out=partials_pair[j])
                     ready = torch.cuda.Event()
                     ready.record(main)
+                    if piped:
+                        loss_done[i] = ready
                     with torch.cuda.stream(comm):
                         comm.wait_event(ready)
-                        dist.all_gather_into_tensor(gathered.view(-1), partials)
-                        ops.loss_finalize_gathered(L, gathered, partials=partials_sum, out=loss_out)     # rank-ordered sum + finalise: one launch
-                        sent = torch.cuda.Event()
-                        sent.record(comm)
-                        gather_done.append(sent)
+                        dist.all_gather_into_tensor(gathered_pair[j].view(-1), partials_pair[j])
+                        ops.loss_finalize_gathered(L, gathered_pair[j], partials=partials_sum, out=loss_out)     # rank-ordered sum + finalise: one launch
+                        gather_done[j] = torch.cuda.Event()
+                        gather_done[j].record(comm)
                     mark()
                     out = decode_beside()
                 else:
-                    ops.loss_partials(L, y_true, y_pred, True, out=partials)
+                    ops.loss_partials(L, yt, y_pred, True, out=partials)
                     work = dist.all_gather_into_tensor(gathered.view(-1), partials, async_op=True)
                     mark()
                     out = decode()
@@ -474,14 +496,20 @@ def _run_ours(args):
             decode_done.append(done)
         return out
 
-    decode_done, gather_done = [], []
+    decode_done, gather_done, xchg_no = [], [None, None], [0]
+    partials_pair = [partials, torch.empty_like(partials)]
+    gathered_pair = [gathered, torch.empty_like(gathered)]
+    step_no, loss_done = [0], [None, None]
+    rstream = torch.cuda.Stream(device=dev)      # --overlap 2: the render stream
+    y_true_pair = [y_true, torch.empty_like(y_true)] if (args.overlap == 2 and args.config == 2) else None
 
     def join():
         main = torch.cuda.current_stream(dev)
         main.wait_stream(side)
         main.wait_stream(comm)
+        main.wait_stream(rstream)
         decode_done.clear()
-        gather_done.clear()
+        gather_done[0] = gather_done[1] = None
 
     n_marks = len(names) + 1
     overlap = bool(args.overlap) and args.config in (2, 4)
@@ -672,8 +700,10 @@ def _run_ours(args):
         "config": {"workload": cfg["workload"], "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"dp{world} (batch shards" + (", one 128-byte exchange overlapped with decode)" if args.config == 2 else ", no collective)"),
                    "l2": f"inputs larger than L2 ({y_pred.numel() * 4 / 1e6:.0f} MB y_pred per GPU per step)",
-                   "schedule": ("decode on a second stream beside render + loss (it only reads y_pred); per-stage times from a "
-                                f"separate sequential pass of the same step ({sequential_ms:.4f} ms/step)") if overlap else "one stream, stages back to back"},
+                   "schedule": ((("render of batch n+1 on its own stream (two y_true buffers) beside loss n; " if (args.overlap == 2 and args.config == 2) else "")
+                                 + "decode on a second stream (it only reads y_pred); every step's render, loss and decode complete "
+                                 "inside the timed region; per-stage times from a "
+                                 f"separate sequential pass of the same step ({sequential_ms:.4f} ms/step)")) if overlap else "one stream, stages back to back"},
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": load_traffic(names[dom].split("(")[0], args.config), "peak_source": peak_src,
                      "whole_step_gbs": whole, "whole_step_frac": whole / peak_gbs, "stages": stages},
@@ -704,7 +734,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
     ap.add_argument("--chunks", type=int, default=4, help="e2e leg: H2D chunks per step")
     ap.add_argument("--spare-sms", type=int, default=-1, help="SMs the decode leaves to the collective (default: 2 when N > 1)")
-    ap.add_argument("--overlap", type=int, default=1, help="configs 2 / 4: 1 = decode on a second stream beside render (+ loss); 0 = one stream")
+    ap.add_argument("--overlap", type=int, default=2, help="configs 2 / 4: 0 = one stream; 1 = decode on a second stream beside render (+ loss); "
+                    "2 (config 2) = also the render on its own stream with two y_true buffers, one batch ahead of the loss")
     ap.add_argument("--check", action="store_true", help="N > 1: compare the sharded loss partials with one GPU, bit for bit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

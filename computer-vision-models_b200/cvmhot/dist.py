@@ -19,7 +19,12 @@ def init_from_env(backend=None):
         os.environ.setdefault("MASTER_PORT", "29500")
         if backend == "nccl":
             torch.cuda.set_device(local)
-            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+            kw = {}
+            try:   # the exchange is 128 bytes: its kernel should get the first SM that frees up, not queue behind full-GPU kernels
+                kw["pg_options"] = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            except (AttributeError, TypeError):
+                pass
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local), **kw)
         else:
             dist.init_process_group(backend, rank=rank, world_size=world)
     return rank, world, local
