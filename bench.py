@@ -707,6 +707,8 @@ def _run_ours(args):
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": load_traffic(names[dom].split("(")[0], args.config), "peak_source": peak_src,
                      "whole_step_gbs": whole, "whole_step_frac": whole / peak_gbs, "stages": stages},
+        "sequential": {"ms_per_step": sequential_ms, "value": B * world / (sequential_ms * 1e-3),
+                       "note": "the same step with all stages back to back on one stream (the pass the stage times come from)"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "note": f"host pinned buffers -> the reference-signature mirror (ProcessImages / CenternetLoss / decode_topk) -> host results, copies inside the timed region "
