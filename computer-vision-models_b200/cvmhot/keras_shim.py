@@ -1,9 +1,11 @@
 """TensorFlow / Keras front for the CUDA loss: `model.compile(loss=CenternetLoss(params), metrics=[loss.class_loss, ...])`
 keeps working literally (reference models/centernet/loss.py:6, models/centernet/train.py:62).
 
-NOT EXERCISED IN THIS REPOSITORY'S TESTS: TensorFlow is not installed in the build image, so this
-module is the binding a maintainer of the reference adds on a box that has TF; everything below the DLPack hand-over is the
-tested torch-facing mirror (cvmhot.models.centernet.loss).  Tensors stay on the GPU: TF -> DLPack -> torch (zero copy),
+NOT EXERCISED AGAINST REAL TENSORFLOW: it is not installed in the build image, so this module is
+the binding a maintainer of the reference adds on a box that has TF.  tests/test_gpu_keras_shim.py drives its glue (DLPack
+hand-over, py_function bodies, the custom-gradient pair, every metric method) through the eager TensorFlow stand-in of
+oracle/tf_shim.py and checks values and gradients against the executed reference; everything below the DLPack hand-over
+is the tested torch-facing mirror (cvmhot.models.centernet.loss).  Tensors stay on the GPU: TF -> DLPack -> torch (zero copy),
 libcvmhot kernels on torch's current stream, result -> DLPack -> TF.  The gradient goes through tf.custom_gradient to the
 hand-written backward kernel (cvm_loss_bwd).
 
@@ -59,7 +61,8 @@ class CenternetLoss(tf.keras.losses.Loss):
             def grad(upstream):
                 def bwd(up):
                     out, ypt = self._saved
-                    (g,) = torch.autograd.grad(out, ypt, grad_outputs=_to_torch(tf.reshape(up, [1]))[0])
+                    (g,) = torch.autograd.grad(out, ypt, grad_outputs=_to_torch(tf.reshape(up, [1]))[0],
+                                               retain_graph=True)      # (a persistent tape may ask twice)
                     torch.cuda.current_stream().synchronize()
                     return _to_tf(g)
                 g = tf.py_function(bwd, [upstream], tf.float32)

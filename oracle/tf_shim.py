@@ -172,6 +172,36 @@ class Loss:
         return out if out.dim() == 0 else out.mean()      # SUM_OVER_BATCH_SIZE on a non-scalar
 
 
+# ---- eager-mode stand-ins for the glue calls of cvmhot/keras_shim.py (tests/test_gpu_keras_shim.py): in eager TF,
+#      tf.py_function runs the Python function at once, tf.custom_gradient returns the forward value and keeps the gradient
+#      function for the tape, and the DLPack hand-over is zero-copy.  Here the "tape" is an attribute on the value.
+def py_function(func, inp, Tout=None):                # tf.py_function, eager
+    out = func(*inp)
+    if isinstance(out, torch.Tensor) and not hasattr(out, "set_shape"):
+        pass
+    return out
+
+
+def custom_gradient(f):                               # tf.custom_gradient, eager: value now, grad_fn kept with it
+    def wrapped(*args):
+        value, grad_fn = f(*args)
+        value._grad_fn_for_tape = grad_fn
+        return value
+    return wrapped
+
+
+def reshape(x, shp):                                  # tf.reshape
+    return _t(x).reshape(tuple(int(v) for v in shp))
+
+
+def _dl_to(t):                                        # tf.experimental.dlpack.to_dlpack: a torch tensor is its own capsule
+    return t
+
+
+def _dl_from(capsule):                                # tf.experimental.dlpack.from_dlpack
+    return torch.utils.dlpack.from_dlpack(capsule)
+
+
 class _Shim(types.ModuleType):
     """A module whose unknown attributes are MagicMocks (so unrelated `from tensorflow.x import y` lines still import)."""
 
@@ -201,6 +231,17 @@ def build_modules():
     nn = _Shim("tensorflow.nn")
     nn.softmax_cross_entropy_with_logits = _softmax_cross_entropy_with_logits
     tf.nn = nn
+    tf.py_function = py_function
+    tf.custom_gradient = custom_gradient
+    tf.reshape = reshape
+    exp_ = _Shim("tensorflow.experimental")
+    dl = _Shim("tensorflow.experimental.dlpack")
+    dl.to_dlpack = _dl_to
+    dl.from_dlpack = _dl_from
+    exp_.dlpack = dl
+    tf.experimental = exp_
+    if not hasattr(torch.Tensor, "set_shape"):        # EagerTensor.set_shape: a static-shape hint, nothing to do here
+        torch.Tensor.set_shape = lambda self, shape: None
     keras = _Shim("tensorflow.keras")
     losses = _Shim("tensorflow.keras.losses")
     losses.Loss = Loss
