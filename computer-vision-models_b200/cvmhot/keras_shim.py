@@ -3,8 +3,8 @@ keeps working literally (reference models/centernet/loss.py:6, models/centernet/
 
 NOT EXERCISED AGAINST REAL TENSORFLOW: it is not installed in the build image, so this module is
 the binding a maintainer of the reference adds on a box that has TF.  tests/test_gpu_keras_shim.py drives its glue (DLPack
-hand-over, py_function bodies, the custom-gradient pair, every metric method) through the eager TensorFlow stand-in of
-oracle/tf_shim.py and checks values and gradients against the executed reference; everything below the DLPack hand-over
+hand-over, py_function bodies, the custom-gradient pair, every metric method) through the eager TensorFlow stand-in that
+the test suite owns and checks values and gradients against the executed reference; everything below the DLPack hand-over
 is the tested torch-facing mirror (cvmhot.models.centernet.loss).  Tensors stay on the GPU: TF -> DLPack -> torch (zero copy),
 libcvmhot kernels on torch's current stream, result -> DLPack -> TF.  The gradient goes through tf.custom_gradient to the
 hand-written backward kernel (cvm_loss_bwd).
