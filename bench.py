@@ -530,8 +530,10 @@ def _run_ours(args):
     barrier()
     e0, e1 = ev(), ev()
     e0.record()
+    t_host = time.perf_counter()
     for k in range(args.steps):
         out = step(ov=overlap)
+    host_issue_ms = (time.perf_counter() - t_host) * 1e3 / args.steps     # Python + launch cost per step (no sync inside)
     join()        # every decode of the timed steps has finished before the closing event
     e1.record()
     barrier()
@@ -554,6 +556,7 @@ def _run_ours(args):
     # (median over the steps: a host-side hiccup - allocator, garbage collection - between two launches of one step would
     # otherwise be booked on whichever stage was waiting for its launch)
     stage_ms = np.median(np.array([[s[i].elapsed_time(s[i + 1]) for i in range(n_marks - 1)] for s in stage_events]), axis=0)
+    sequential_ms = float(np.median([s[0].elapsed_time(s[n_marks - 1]) for s in stage_events]))     # (median, for the same reason)
 
     # ---- the backward of the loss as its own timed stage (config 2; not part of the metric: reads y_true + y_pred, writes the gradient) ----
     extra = {}
@@ -707,6 +710,7 @@ def _run_ours(args):
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": load_traffic(names[dom].split("(")[0], args.config), "peak_source": peak_src,
                      "whole_step_gbs": whole, "whole_step_frac": whole / peak_gbs, "stages": stages},
+        "host_issue_ms_per_step": host_issue_ms,
         "sequential": {"ms_per_step": sequential_ms, "value": B * world / (sequential_ms * 1e-3),
                        "note": "the same step with all stages back to back on one stream (the pass the stage times come from)"},
         "cpu_baseline": cpu,

@@ -49,6 +49,7 @@ constexpr int kTestThreads = kTestWarps * 32;
 constexpr int kLoaderWarp = kTestWarps + kScanWarps;
 constexpr int kThreads = (kLoaderWarp + 1) * 32;
 constexpr int kMergeThreads = 256;
+constexpr int kMergeTab = 192;     // scan CTAs whose image ranges travel in the merge kernel's parameters
 constexpr int kMaxSlots = kScanWarps;   // ring depth (granules): one slot per active scanner warp
 constexpr int kCtr = 2 * kMaxSlots;
 constexpr int kMaxT = 1024;        // pixels per granule (a scanner lane keeps one hit bit per pixel of its granule: 32 x 32)
@@ -1478,9 +1479,13 @@ struct MergeParams {
     float* centers;
     float* boxes;
     float* track;
+    // first / last image of every scan CTA (host-computed, grid <= kMergeTab): the merge finds the CTAs of its image by
+    // counting instead of 64-bit divisions (~2 us of serial latency at the top of each of these tiny CTAs)
+    int use_tab;
+    int first_img[kMergeTab], last_img[kMergeTab];
 };
 
-__global__ void __launch_bounds__(kMergeThreads) decode_merge_kernel(const MergeParams p) {
+__global__ void __launch_bounds__(kMergeThreads) decode_merge_kernel(const __grid_constant__ MergeParams p) {
     __shared__ unsigned int hist[256];
     __shared__ int s_misc[4];
     __shared__ unsigned long long s_thr;
@@ -1496,19 +1501,30 @@ __global__ void __launch_bounds__(kMergeThreads) decode_merge_kernel(const Merge
     // the scan CTAs whose granule range [g*n/G, (g+1)*n/G) overlaps this image's granules [lo, hi) (every CTA has at least
     // one granule: the grid never exceeds their number)
     const long long n_ch = p.n_steps, G = p.grid;
-    if (tid == 0) {   // (64-bit divisions: once per CTA)
-        const long long lo = (long long)b * p.spi, hi = lo + p.spi;
-        long long gf = lo * G / n_ch;
-        while (gf + 1 < G && (gf + 1) * n_ch / G <= lo) ++gf;
-        long long gl = gf;
-        while (gl + 1 < G && (gl + 1) * n_ch / G < hi) ++gl;
-        s_g[0] = (int)gf;
-        s_g[1] = (int)gl;
-        s_need = 0u;
-        s_total = 0;
+    long long g_first, g_last;
+    if (p.use_tab) {   // the CTAs' image ranges are monotone: count the ones that end before / start at or before this image
+        if (tid == 0) {
+            s_need = 0u;
+            s_total = 0;
+        }
+        g_first = __syncthreads_count(tid < p.grid && p.last_img[tid < p.grid ? tid : 0] < b);
+        g_last = __syncthreads_count(tid < p.grid && p.first_img[tid < p.grid ? tid : 0] <= b) - 1;
+    } else {
+        if (tid == 0) {   // (64-bit divisions: once per CTA)
+            const long long lo = (long long)b * p.spi, hi = lo + p.spi;
+            long long gf = lo * G / n_ch;
+            while (gf + 1 < G && (gf + 1) * n_ch / G <= lo) ++gf;
+            long long gl = gf;
+            while (gl + 1 < G && (gl + 1) * n_ch / G < hi) ++gl;
+            s_g[0] = (int)gf;
+            s_g[1] = (int)gl;
+            s_need = 0u;
+            s_total = 0;
+        }
+        group_sync(kMergeThreads);
+        g_first = s_g[0];
+        g_last = s_g[1];
     }
-    group_sync(kMergeThreads);
-    const long long g_first = s_g[0], g_last = s_g[1];
     const int n_over = (int)(g_last - g_first + 1);
     // Segments that ran behind a PROVISIONAL threshold (predicted from the image before, see flush_segment) published
     // every peak at or above it; the prediction holds for this image iff at least K of all its published peaks reach the
@@ -1516,10 +1532,11 @@ __global__ void __launch_bounds__(kMergeThreads) decode_merge_kernel(const Merge
     // belong to the top K).  One thread per segment fetches its record (one round trip for all of them).
     for (int t = tid; t < n_over; t += kMergeThreads) {
         const long long g = g_first + t;
-        const SegMeta mt = p.segmeta[(size_t)g * p.max_segs + (int)(b - (g * n_ch / G) / p.spi)];
+        const int seg = b - (p.use_tab ? p.first_img[g] : (int)((g * n_ch / G) / p.spi));
+        const SegMeta mt = p.segmeta[(size_t)g * p.max_segs + seg];
         if (t < kMergeThreads) {
             s_cnt[t] = mt.count;
-            s_off[t] = (int)((size_t)g * p.max_segs + (int)(b - (g * n_ch / G) / p.spi));
+            s_off[t] = (int)((size_t)g * p.max_segs + seg);
         }
         if (!mt.verified) atomicMax(&s_need, mt.thr_bits);
         atomicAdd(&s_total, mt.count);
@@ -1544,7 +1561,7 @@ __global__ void __launch_bounds__(kMergeThreads) decode_merge_kernel(const Merge
         n = base;
     } else {
         for (long long g = g_first; g <= g_last; ++g) {
-            const int seg = (int)(b - (g * n_ch / G) / p.spi);
+            const int seg = b - (p.use_tab ? p.first_img[g] : (int)((g * n_ch / G) / p.spi));
             const size_t o = (size_t)g * p.max_segs + seg;
             const int cnt = p.segmeta[o].count;
             if (n + cnt > kMergeCap) {   // cnt <= seg_keys <= kMergeCap / 4, so n > K here
@@ -1922,6 +1939,12 @@ int decode_impl(const cvm_layout* L, const float* y_pred, int pred_stride, int B
     m.centers = centers;
     m.boxes = boxes;
     m.track = track;
+    m.use_tab = t.grid <= kMergeTab;
+    for (int g = 0; m.use_tab && g < t.grid; ++g) {   // the scan's split of the granules: CTA g owns [g*n/G, (g+1)*n/G)
+        const long long lo = (long long)g * t.n_gran / t.grid, hi = (long long)(g + 1) * t.n_gran / t.grid - 1;
+        m.first_img[g] = (int)(lo / t.gpi);
+        m.last_img[g] = (int)(hi / t.gpi);
+    }
     CVM_SMEM_ATTR_ONCE(decode_merge_kernel, ((size_t)kMergeCap + 3 * (size_t)kMaxK) * 8);
     // (tried: programmatic dependent launch of the merge kernel, griddepcontrol.launch_dependents at the top of the scan:
     // 0.143 ms instead of 0.139 for the pair - the early-resident merge CTAs are in the way more than the launch gap costs)
