@@ -265,3 +265,34 @@ def test_render_many_small_images_per_cta(cuda, H, W, B):
         assert np.array_equal(y[s:s + step], part), s
     for b in list(range(0, B, 131)) + [3, 53, 60, B - 1]:
         _close(y[b], render_np.render_image(Lo, boxes[b], cls[b], ign[b]))
+
+
+def test_render_repeatable_bitwise(cuda):
+    """The builder groups and the setup group of a CTA only meet through flags and named barriers: a missing hand-over would
+    show up as run-to-run differences.  40 launches of the BASELINE shape (96 images: CTAs with one, two and three images)
+    must be bitwise identical, also while another stream keeps the GPU busy."""
+    import bench
+    from cvmhot import ops
+    from cvmhot.layout import layout_from_params
+    from cvmhot.models.centernet.processor import pack_boxes, pack_objects
+    B = 96
+    p = _params(10, True, 128, 384)
+    L = layout_from_params(p)
+    boxes, cls, ign = bench.gen_objects(0, B)
+    rec, offs = pack_objects(list(boxes), list(cls))
+    ign_rec, ign_offs = pack_boxes(list(ign))
+    objs_d = ops.to_device_records(rec, ops.OBJ_DTYPE, cuda)
+    offs_d = torch.from_numpy(offs).to(cuda)
+    ign_d = ops.to_device_records(ign_rec, ops.BOX_DTYPE, cuda)
+    ioffs_d = torch.from_numpy(ign_offs).to(cuda)
+    ref = ops.render_gt(L, objs_d, offs_d, B, ign_d, ioffs_d).clone()
+    noise = torch.empty(2 ** 26, device=cuda)
+    side = torch.cuda.Stream(device=cuda)
+    out = torch.empty_like(ref)
+    for it in range(40):
+        if it % 2:
+            with torch.cuda.stream(side):
+                noise.fill_(float(it))
+        ops.render_gt(L, objs_d, offs_d, B, ign_d, ioffs_d, out=out)
+        assert torch.equal(out, ref), it
+    torch.cuda.synchronize()
