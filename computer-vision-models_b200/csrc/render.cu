@@ -308,7 +308,10 @@ __device__ __forceinline__ void setup_main(const RenderParams& p, RenderShared& 
         setup_image(p, S, S.set[k & 1], img0 + k, st, kST, kGroups + 1);
         fence_cta_r();
         bar_group(kGroups + 1, kST);   // (also: S.own / S.used are free for the next image)
-        if (st == 0) S.ready = k + 1;
+        if (st == 0) {
+            fence_cta_r();   // release: the group's writes, observed through the barrier, before the flag
+            S.ready = k + 1;
+        }
     }
 }
 
