@@ -313,14 +313,17 @@ def make_pred(torch, dev, g, B, Hm, Wm, L, C_total, boxes, cls):
 
 
 def run_ours(args):
-    """The whole benchmark runs on a HIGH-priority stream; the decode's second stream has default priority: the block
-    scheduler then gives render / loss CTAs the SMs first and the decode fills in behind them - at the tails, and (N > 1)
-    beside the exchange of the loss partials at the end of the step."""
+    """Stream priorities (measured, B200): with the render on the main stream (configs[3], --overlap 0 / 1) the main stream
+    is HIGH priority and the decode's stream default - the block scheduler gives render / loss CTAs the SMs first and the
+    decode fills in behind them.  With the three-stream schedule of configs[1] (--overlap 2) the RENDER stream is the high-
+    priority one (0.491 against 0.496 ms per step with the loss stream high): the next batch's ground truth is the work
+    that must never wait, the loss of the current batch takes what it frees."""
     import torch
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local)
-    with torch.cuda.stream(torch.cuda.Stream(device=torch.device("cuda", local), priority=-1)):
+    piped = args.config == 2 and args.overlap == 2
+    with torch.cuda.stream(torch.cuda.Stream(device=torch.device("cuda", local), priority=0 if piped else -1)):
         _run_ours(args)
 
 
@@ -500,7 +503,7 @@ def _run_ours(args):
     partials_pair = [partials, torch.empty_like(partials)]
     gathered_pair = [gathered, torch.empty_like(gathered)]
     step_no, loss_done = [0], [None, None]
-    rstream = torch.cuda.Stream(device=dev)      # --overlap 2: the render stream
+    rstream = torch.cuda.Stream(device=dev, priority=-1)      # --overlap 2: the render stream (see run_ours)
     y_true_pair = [y_true, torch.empty_like(y_true)] if (args.overlap == 2 and args.config == 2) else None
 
     def join():
